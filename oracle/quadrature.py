@@ -44,7 +44,7 @@ def gauss_jacobi(cell: str, degree: int):
         for j in range(m):
             for k in range(m):
                 pts.append((x0[i], x1[j] * (1.0 - x0[i]), x2[k] * (1.0 - x0[i]) * (1.0 - x1[j])))
-                wts.append(w0[i] * w1[j] * w2[k] * 0.125 * 0.125 * 0.5)
+                wts.append(w0[i] * w1[j] * w2[k] * 0.125 * 0.25 * 0.5)
     return np.array(pts), np.array(wts)
 
 

@@ -1,0 +1,157 @@
+// Multi-GPU plumbing: one process per GPU, NCCL over NVLink/NVSwitch for the two exchanges this path
+// has -- the owner->ghost halo of a mixed vector (Vec.ghostUpdate(INSERT, FORWARD),
+// src/lvpp/problem.py:56,58,71,73) and the scalar all-reduces of norms / Krylov dot products
+// (PETSc VecNorm/VecDot and comm.allreduce at examples/01_obstacle_problem/obstacle_pg.py:50).
+// Owned rows are assembled completely from owned + ghost cells, so neither the residual reverse
+// scatter (problem.py:66) nor Mat.assemble() (problem.py:77) needs communication.
+//
+// NCCL is resolved with dlopen at lvpp_comm_init time so that the single-GPU library has no link
+// dependency on it (the process usually has torch's libnccl.so.2 loaded already).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+
+#include "lvpp_internal.cuh"
+
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+} g_nccl;
+
+int load_nccl() {
+  if (g_nccl.lib) return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) {
+    lvpp_set_error("cannot dlopen libnccl.so.2: %s", dlerror());
+    return LVPP_E_COMM;
+  }
+#define SYM(field, name)                                                    \
+  *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, name);                       \
+  if (!g_nccl.field) { lvpp_set_error("missing NCCL symbol %s", name); g_nccl.lib = nullptr; return LVPP_E_COMM; }
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(AllReduce, "ncclAllReduce");
+  SYM(Send, "ncclSend");
+  SYM(Recv, "ncclRecv");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  return 0;
+}
+}  // namespace
+
+#define NCK(call)                                                                                  \
+  do {                                                                                             \
+    ncclResult_t r_ = (call);                                                                      \
+    if (r_ != ncclSuccess) {                                                                       \
+      lvpp_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_));      \
+      return LVPP_E_COMM;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+__global__ void k_pack(int64_t n, const int32_t* __restrict__ nodes, const double2* __restrict__ v,
+                       double2* __restrict__ buf) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
+    buf[p] = v[nodes[p]];
+}
+__global__ void k_unpack(int64_t n, const int32_t* __restrict__ nodes, const double2* __restrict__ buf,
+                         double2* __restrict__ v) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
+    v[nodes[p]] = buf[p];
+}
+
+extern "C" int lvpp_comm_unique_id(uint8_t* h_id128) {
+  if (!h_id128) { lvpp_set_error("null argument"); return LVPP_E_INVALID; }
+  CKR(load_nccl());
+  ncclUniqueId id;
+  NCK(g_nccl.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(h_id128, &id, 128);
+  return LVPP_OK;
+}
+
+extern "C" int lvpp_comm_init(lvpp_handle h, const uint8_t* h_id128, int32_t rank, int32_t nranks) {
+  if (!h || !h_id128 || nranks < 1 || rank < 0 || rank >= nranks) { lvpp_set_error("bad argument"); return LVPP_E_INVALID; }
+  CK(cudaSetDevice(h->device));
+  CKR(load_nccl());
+  ncclUniqueId id;
+  memcpy(&id, h_id128, 128);
+  ncclComm_t comm;
+  NCK(g_nccl.CommInitRank(&comm, nranks, id, rank));
+  h->nccl_comm = (void*)comm;
+  h->rank = rank;
+  h->nranks = nranks;
+  // global row count
+  double* tmp = h->scal->red;
+  double rows = 2.0 * (double)h->Vown;
+  CK(cudaMemcpyAsync(tmp, &rows, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CKR(lvpp_allreduce_sum(h, tmp, 1));
+  CK(cudaMemcpyAsync(&rows, tmp, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->global_rows = (int64_t)(rows + 0.5);
+  return LVPP_OK;
+}
+
+void lvpp_comm_destroy(lvpp_problem* h) {
+  if (h->nccl_comm && g_nccl.CommDestroy) {
+    g_nccl.CommDestroy((ncclComm_t)h->nccl_comm);
+    h->nccl_comm = nullptr;
+  }
+}
+
+int lvpp_allreduce_sum(lvpp_problem* h, double* d_buf, int n) {
+  if (h->nranks <= 1) return 0;
+  if (!h->nccl_comm) { lvpp_set_error("communicator not initialised"); return LVPP_E_COMM; }
+  NCK(g_nccl.AllReduce(d_buf, d_buf, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
+  return 0;
+}
+
+int lvpp_halo_forward_impl(lvpp_problem* h, double* d_v) {
+  if (h->nranks <= 1 || h->num_neighbors == 0) return 0;
+  if (!h->nccl_comm) { lvpp_set_error("communicator not initialised"); return LVPP_E_COMM; }
+  const int64_t ns = h->send_ptr.back(), nr = h->recv_ptr.back();
+  if (ns > 0) {
+    LAUNCH(h, k_pack, lvpp_grid(ns, 256, 4), 256, 0, ns, h->send_nodes, (const double2*)d_v, (double2*)h->send_buf);
+    CK(cudaGetLastError());
+  }
+  NCK(g_nccl.GroupStart());
+  for (int b = 0; b < h->num_neighbors; ++b) {
+    const int64_t s0 = h->send_ptr[b], s1 = h->send_ptr[b + 1], r0 = h->recv_ptr[b], r1 = h->recv_ptr[b + 1];
+    if (s1 > s0)
+      NCK(g_nccl.Send(h->send_buf + 2 * s0, (size_t)(2 * (s1 - s0)), ncclDouble, h->neighbor_ranks[b],
+                      (ncclComm_t)h->nccl_comm, h->stream));
+    if (r1 > r0)
+      NCK(g_nccl.Recv(h->recv_buf + 2 * r0, (size_t)(2 * (r1 - r0)), ncclDouble, h->neighbor_ranks[b],
+                      (ncclComm_t)h->nccl_comm, h->stream));
+  }
+  NCK(g_nccl.GroupEnd());
+  if (nr > 0) {
+    LAUNCH(h, k_unpack, lvpp_grid(nr, 256, 4), 256, 0, nr, h->recv_nodes, (const double2*)h->recv_buf, (double2*)d_v);
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+
+extern "C" int lvpp_halo_forward(lvpp_handle h, double* d_v) {
+  if (!h || !d_v) { lvpp_set_error("null argument"); return LVPP_E_INVALID; }
+  CK(cudaSetDevice(h->device));
+  CKR(lvpp_halo_forward_impl(h, d_v));
+  CK(cudaStreamSynchronize(h->stream));
+  return LVPP_OK;
+}

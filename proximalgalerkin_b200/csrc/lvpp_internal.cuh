@@ -1,0 +1,192 @@
+// Internal definitions shared by the translation units of liblvpp_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <utility>
+#include <vector>
+
+#include "../../include/lvpp_b200.h"
+
+#define LVPP_MAX_NQ 64
+#define LVPP_MAX_ROW 255      // longest scalar row (uint8 slot offsets)
+#define LVPP_SLICE 32         // sliced-ELL slice height = warp width
+#define LVPP_NUM_SMS 148      // B200
+#define LVPP_COL_BC 0x80000000u  // bit 31 of a stored column index: column node is Dirichlet (u)
+
+void lvpp_set_error(const char* fmt, ...);
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      lvpp_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));    \
+      return LVPP_E_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+#define CKR(call)            \
+  do {                       \
+    int r_ = (call);         \
+    if (r_ != 0) return r_;  \
+  } while (0)
+
+// every kernel launch of this library goes through here so that launches can be counted
+#define LAUNCH(h, kern, grid, block, smem, ...)                         \
+  do {                                                                  \
+    kern<<<(grid), (block), (smem), (h)->stream>>>(__VA_ARGS__);        \
+    (h)->launches++;                                                    \
+  } while (0)
+
+// device-resident scalars of the Krylov recurrence (no host round trips inside an iteration)
+struct KryScal {
+  double gamma0, gamma1, eta, s0, s1, c0, c1;
+  double r0;
+  double delta;
+  double cv1, cv0;        // Lanczos three-term coefficients
+  double inv_gamma1;      // scaling of the next Lanczos vector
+  double inv_gamma_w;     // scaling used by the direction update of the current iteration
+  double a1, a2, a3, tau; // direction / solution update coefficients
+  double tol;
+  double rtol, atol;
+  double red[8];          // reduction results (allreduced across ranks)
+  int conv, skip, its, reason, maxit;
+};
+
+struct lvpp_problem {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int tdim = 0, nld = 0, nq = 0, nsym = 0;
+  int64_t V = 0, Vown = 0, C = 0, Cown = 0;
+  double f = 0.0, alpha = 1.0;
+  int64_t launches = 0;
+  int64_t device_bytes = 0;
+  std::vector<std::pair<void*, size_t>> allocs;
+
+  // mesh
+  double* coords = nullptr;    // [V * tdim]
+  int32_t* cells = nullptr;    // [C * nld]
+  double* adetJ = nullptr;     // [C] |det J|
+  double* tab = nullptr;       // device tables: w[nq], phi[nq*nld], dphi[nq*nld*tdim], qpts[nq*tdim]
+  // incidence lists of the owned nodes (row gather map)
+  int64_t* inc_ptr = nullptr;  // [Vown + 1]
+  uint32_t* inc_val = nullptr; // [C * nld] cell * nld + local index, grouped by node, cell-sorted
+  uint8_t* inc_k = nullptr;    // [C * nld * nld] slot offset within the row for every local column
+  // scalar pattern in sliced ELL
+  int64_t nslices = 0, sell_slots = 0, scalar_nnz = 0;
+  int32_t maxw = 0;
+  int64_t* slice_ptr = nullptr; // [nslices + 1]
+  int32_t* rowlen = nullptr;    // [Vown]
+  int64_t* rowptr = nullptr;    // [Vown + 1] scalar CSR row pointer (export)
+  uint32_t* col = nullptr;      // [sell_slots] column node | LVPP_COL_BC
+  uint8_t* diag_k = nullptr;    // [Vown]
+  double *K = nullptr, *M = nullptr, *D = nullptr;  // [sell_slots]
+  double* De = nullptr;         // [C * nsym] element scratch (cell-major)
+  // node data
+  uint8_t* bc_flag = nullptr;   // [V]
+  double* bc_val = nullptr;     // [V]
+  double* bobs = nullptr;       // [Vown] int phi_obs phi_i
+  double* fvec = nullptr;       // [Vown] int phi_i
+  double* xk = nullptr;         // [2V] previous proximal iterate
+  // work vectors [2V]
+  double *F = nullptr, *y = nullptr, *va = nullptr, *vb = nullptr, *Az = nullptr, *za = nullptr,
+         *zb = nullptr, *wa = nullptr, *wb = nullptr, *pinv = nullptr, *xhost_stage = nullptr;
+  double* partials = nullptr;   // [npartials * 8]
+  int npartials = 0;
+  KryScal* scal = nullptr;      // device
+  KryScal* scal_host = nullptr; // pinned
+  double* red_host = nullptr;   // pinned [16]
+  double* flush = nullptr;      // L2 flush scratch
+  size_t flush_bytes = 0;
+  bool jac_valid = false;
+  // Newton state
+  double fnorm = 0.0;
+  // stats
+  int64_t krylov_its = 0, newton_steps = 0, residual_evals = 0;
+  double t_assembly_ms = 0.0, t_krylov_ms = 0.0, last_spmv_ms = 0.0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // communication
+  int rank = 0, nranks = 1;
+  void* nccl_comm = nullptr;
+  int num_neighbors = 0;
+  std::vector<int32_t> neighbor_ranks;
+  std::vector<int64_t> send_ptr, recv_ptr;
+  int32_t* send_nodes = nullptr;  // device
+  int32_t* recv_nodes = nullptr;  // device
+  double* send_buf = nullptr;     // device [2 * nsend]
+  double* recv_buf = nullptr;     // device [2 * nrecv]
+  int64_t global_rows = 0;
+};
+
+template <class T>
+int lvpp_dalloc(lvpp_problem* h, T** p, size_t n, bool zero = true) {
+  size_t bytes = (n ? n : 1) * sizeof(T);
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, bytes);
+  if (e != cudaSuccess) {
+    lvpp_set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    return LVPP_E_CUDA;
+  }
+  if (zero) {
+    e = cudaMemsetAsync(q, 0, bytes, h->stream);
+    if (e != cudaSuccess) {
+      lvpp_set_error("cudaMemset failed: %s", cudaGetErrorString(e));
+      return LVPP_E_CUDA;
+    }
+  }
+  h->allocs.push_back(std::make_pair(q, bytes));
+  h->device_bytes += (int64_t)bytes;
+  *p = (T*)q;
+  return 0;
+}
+int lvpp_dfree(lvpp_problem* h, void* p);
+
+static inline int lvpp_grid(int64_t work_items, int block, int per_sm = 8) {
+  int64_t need = (work_items + block - 1) / block;
+  int64_t cap = (int64_t)LVPP_NUM_SMS * per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// ---- device helpers -------------------------------------------------------------------------
+__device__ __forceinline__ double lvpp_warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+// deterministic block sum (fixed shuffle tree); result valid in thread 0. sm: >= 32 doubles
+template <int NT>
+__device__ __forceinline__ double lvpp_block_sum(double v, double* sm) {
+  v = lvpp_warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = lane < (NT / 32) ? sm[lane] : 0.0;
+    r = lvpp_warp_sum(r);
+  }
+  return r;
+}
+__host__ __device__ __forceinline__ int lvpp_sym(int a, int b, int nld) {
+  // index of (a, b), a <= b, in the packed upper triangle
+  return a * nld - (a * (a - 1)) / 2 + (b - a);
+}
+
+// ---- cross-TU entry points --------------------------------------------------------------------
+int lvpp_build_pattern(lvpp_problem* h);                      // setup.cu
+int lvpp_build_constant_operators(lvpp_problem* h, const lvpp_obstacle_desc* d);  // assembly.cu
+int lvpp_eval_residual(lvpp_problem* h, const double* d_x, double* d_F, bool want_norm);  // assembly.cu
+int lvpp_apply_jacobian(lvpp_problem* h, const double* d_v, double* d_y, const double* inv_scale,
+                        double* partials, const int* skip_flag);                    // assembly.cu
+int lvpp_reduce_partials(lvpp_problem* h, int nvals, double* d_out);  // assembly.cu
+int lvpp_allreduce_sum(lvpp_problem* h, double* d_buf, int n);       // comm.cu
+int lvpp_halo_forward_impl(lvpp_problem* h, double* d_v);            // comm.cu
+int lvpp_minres(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_newton_opts* o,
+                int32_t* its, int32_t* reason, double* rnorm);       // krylov.cu
+int lvpp_build_preconditioner(lvpp_problem* h, const lvpp_newton_opts* o);  // krylov.cu
+void lvpp_comm_destroy(lvpp_problem* h);                             // comm.cu
