@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""LVPP Newton-step throughput on B200 (BASELINE.json metric) -- see DESIGN.md section "Measurement".
+
+A "step" is one Newton step of the LVPP obstacle solve (Krylov solve of the saddle-point system,
+fused update + norms, residual and Jacobian assembly at the new iterate; outer-loop work --
+observables, alpha update, sol_k <- sol -- is inside the timed region when it falls between steps).
+Workload at N GPUs: the 3-D P1 obstacle problem on [-1,1]^2 x [-N,N], n x n x (n N) cubes x 6 Kuhn
+tetrahedra, one z-slab per GPU (weak scaling; n = 215 -> 20.2 M rows per GPU), started from the zero
+iterate with the reference's CI parameters (double-exponential alpha, alpha_max 1e2, tol 1e-4,
+SNES rtol 1e-6).  Warm-up steps are the first W Newton steps of that solve; the K timed steps
+continue it.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n 215] [--impl b200|reference]
+
+--impl reference times the CPU restatement of the reference algorithm (oracle/: numpy assembly +
+SuperLU in place of dolfinx + MUMPS; the real stack is not installable here) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "lvpp_newton_dofs_per_sec"
+UNIT = "DOFs/s"  # rows of the mixed Newton system x Newton steps / second
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_newton_steps(n_cpu, steps, warmup):
+    """Times `steps` Newton steps of the oracle's LVPP solve (after `warmup`) on an n_cpu^3 mesh.
+    Returns (DOFs/s, seconds, rows, steps_done)."""
+    import numpy as np
+
+    from oracle import lvpp_driver, mesh as omesh, obstacle as oobs, snes as osnes
+
+    orc = oobs.ObstacleOracle(omesh.box_kuhn(n_cpu, n_cpu, n_cpu))
+    x = np.zeros(orc.num_rows)
+    xk = x.copy()
+    alpha_k, alpha, k = 1, 1.0, 0
+    done, t_timed, t0 = 0, 0.0, None
+    total = steps + warmup
+    while done < total:
+        alpha, alpha_k = lvpp_driver.alpha_schedule("double_exponential", k, alpha_k, 1e2, alpha_current=alpha)
+        # one Newton step at a time so that exactly `steps` are timed
+        F = orc.assemble_residual(x, xk, alpha)
+        fnorm0 = np.linalg.norm(F)
+        it = 0
+        while done < total:
+            if done == warmup and t0 is None:
+                t0 = time.perf_counter()
+            import scipy.sparse.linalg as spla
+
+            y = spla.splu(orc.jacobian(x, alpha).tocsc()).solve(F)
+            x = x - y
+            F = orc.assemble_residual(x, xk, alpha)
+            fnorm = np.linalg.norm(F)
+            it += 1
+            done += 1
+            if osnes.converged_default(it, np.linalg.norm(x), np.linalg.norm(y), fnorm, fnorm0 * 1e-6, fnorm0, 1e-50, 1e-8, 1e4):
+                break
+        obs = orc.observables(x, xk, alpha)
+        if np.sqrt(obs[4]) < 1e-4:
+            break
+        xk = x.copy()
+        k += 1
+    t_timed = time.perf_counter() - t0 if t0 is not None else float("nan")
+    nsteps = done - warmup
+    return orc.num_rows * nsteps / t_timed, t_timed, orc.num_rows, nsteps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_cpu = args.n_cpu
+    val, secs, rows, nsteps = cpu_newton_steps(n_cpu, args.steps, args.warmup)
+    sample = (f"{nsteps} Newton steps of the same LVPP obstacle solve on a {n_cpu}^3-cube Kuhn mesh ({rows} rows), "
+              "numpy assembly + scipy SuperLU (stand-in for dolfinx + MUMPS), 1 thread")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": nsteps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(nsteps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"3-D P1 obstacle LVPP, CPU sample n={n_cpu} ({rows} rows); GPU arm runs n={args.n} per GPU"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "newton_steps_per_sec": nsteps / secs,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import proximalgalerkin_b200 as lvpp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = args.n
+    t_setup = time.perf_counter()
+    msh = lvpp.mesh.create_box(n, n, n * world, lo=(-1.0, -1.0, -float(world)), hi=(1.0, 1.0, float(world)),
+                               rank=rank, nranks=world)
+    opts = {"ksp_rtol": args.ksp_rtol, "ksp_max_it": 200000}
+    st = lvpp.obstacle_pg.LvppStepper(msh, 1, "double_exponential", 1e2, 1e-4, petsc_options=opts)
+    dev = st.dev
+    stats0 = dev.stats()
+    t_setup = time.perf_counter() - t_setup
+    rows_global = stats0["num_rows"]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up: the first W Newton steps of the solve
+    for _ in range(args.warmup):
+        if not st.step():
+            break
+    # ---- timed region: exactly K Newton steps
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    s0 = dev.stats()
+    barrier()
+    dev.timer_start()
+    t0 = time.perf_counter()
+    done = 0
+    while done < args.steps:
+        alive = st.step()
+        done += 1
+        if not alive:
+            break
+    dev_ms = dev.timer_stop()
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    s1 = dev.stats()
+    t = torch.tensor([dev_ms / 1e3, wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs, wall = float(t[0]), float(t[1])
+    value = rows_global * done / secs
+    kry = s1["krylov_iterations"] - s0["krylov_iterations"]
+    launches = s1["kernel_launches"] - s0["kernel_launches"]
+
+    # ---- roofline of the dominant kernel (J*v): launches sampled with CUDA events inside the timed solves
+    n_s = s1["spmv_samples"] - s0["spmv_samples"]
+    spmv_ms = (s1["spmv_sampled_ms"] - s0["spmv_sampled_ms"]) / max(n_s, 1)
+    V_own = stats0["local_rows"] // 2
+    slots = stats0["sell_slots"]
+    # compulsory bytes of one J*v launch in the stored format: per slot col(4) + K,M,D (24);
+    # per node: gathered v (16) + own v (16, L2-resident) counted once as 16, y (16), bc flag (1), slice ptr (8/32)
+    spmv_bytes = 28 * slots + (16 + 16 + 1 + 0.25) * V_own
+    peak, peak_src = measured_peak()
+    achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if n_s else None
+    traffic = None
+    tf = ROOT / "profiles" / "spmv_traffic.json"
+    if tf.exists():
+        try:
+            tj = json.loads(tf.read_text())
+            if int(tj.get("n", -1)) == n:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    roofline = {
+        "bound": "hbm", "kernel": "k_block_op<0> (J*v, 2x2-block sliced-ELL)", "achieved": achieved, "peak": peak,
+        "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms, "launches_sampled": n_s,
+        "csr_equivalent_bytes": 12 * stats0["nnz"] + 16 * stats0["local_rows"] + 8 * (stats0["local_rows"] + 1),
+        "share_of_step": (spmv_ms * kry) / (secs * 1e3) if secs > 0 else None,
+    }
+
+    # ---- e2e: the same solve through NonlinearProblem.solve() on host buffers (H2D of sol and sol_k,
+    # D2H of sol inside the timed region), whole outer iterations until >= K Newton steps
+    e2e = None
+    if not args.no_e2e:
+        s = st.s
+        sol, sol_k, alpha, problem = s["sol"], s["sol_k"], s["alpha"], s["problem"]
+        sol.x.array[:] = 0.0
+        sol_k.x.array[:] = 0.0
+        alpha.value, alpha_k, k, steps_e2e = 1.0, 1, 0, 0
+        n_solves = 0
+        barrier()
+        te = time.perf_counter()
+        while steps_e2e < args.steps:
+            alpha.value, alpha_k = lvpp.obstacle_pg.alpha_update("double_exponential", k, alpha.value, alpha_k, 1e2)
+            problem.solve()
+            steps_e2e += problem.solver.getIterationNumber()
+            n_solves += 1
+            dev.x.set(sol.x.array)
+            obs = dev.observables(dev.x)
+            if np.sqrt(obs[4]) < 1e-4:
+                break
+            sol_k.x.array[:] = sol.x.array[:]
+            k += 1
+        barrier()
+        te = time.perf_counter() - te
+        t = torch.tensor([te], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        te = float(t[0])
+        vec_bytes = 8 * dev.n
+        e2e = {
+            "value": rows_global * steps_e2e / te, "unit": UNIT, "steps": steps_e2e, "seconds": te,
+            "h2d_bytes_per_step": 3 * vec_bytes * n_solves / max(steps_e2e, 1),  # sol, sol_k (+ sol for observables)
+            "d2h_bytes_per_step": vec_bytes * n_solves / max(steps_e2e, 1),
+            "api": "NonlinearProblem.solve() per proximal step, host numpy buffers",
+        }
+
+    # ---- assembly kernels (reported, not the headline)
+    asm = None
+    if rank == 0 and not args.no_aux:
+        F = lvpp.DeviceVector(dev.n, dev.device)
+        a, b, c = dev.time_assembly(dev.x, F, reps=3)
+        asm = {"cell_exp_ms": a, "row_gather_ms": b, "residual_ms": c}
+
+    # ---- CPU baseline on this box's host cores (bounded sample)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        val, secs_c, rows_c, ns = cpu_newton_steps(args.n_cpu, 5, 1)
+        cpu = {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{ns} Newton steps of the same LVPP solve on a {args.n_cpu}^3-cube Kuhn mesh ({rows_c} rows), "
+                         f"numpy assembly + SuperLU (oracle/), {secs_c:.1f} s; host has {os.cpu_count()} cores"}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": done, "warmup": args.warmup,
+            "ms_per_step": 1e3 * secs / max(done, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"3-D P1 obstacle LVPP (configs[1]): {n}x{n}x{n * world} cubes x 6 tets, "
+                                   f"{rows_global} rows, {stats0['nnz']} nnz/GPU (CSR-equivalent)",
+                       "n": n, "rows": rows_global, "alpha_scheme": "double_exponential", "alpha_max": 1e2,
+                       "snes_rtol": 1e-6, "ksp": "MINRES + block-Jacobi/Schur-diag", "ksp_rtol": args.ksp_rtol,
+                       "l2": "operator (>=4 GB) and vectors exceed the 126 MB L2; no flush needed" if n >= 100 else
+                             "inputs fit L2: kernel-level numbers are L2-warm",
+                       "parallelism": f"slab{world}"},
+            "newton_steps_per_sec": done / secs, "krylov_iterations": kry, "wall_s": wall, "setup_s": t_setup,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "assembly": asm, "device_bytes": stats0["device_bytes"], "outer_history": st.history,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--n", type=int, default=215, help="cubes per axis per GPU")
+    ap.add_argument("--n-cpu", dest="n_cpu", type=int, default=16, help="cubes per axis of the CPU sample")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ksp-rtol", dest="ksp_rtol", type=float, default=1e-12)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-aux", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

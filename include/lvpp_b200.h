@@ -123,6 +123,8 @@ typedef struct lvpp_stats {
   double t_assembly_ms;      /* cumulative CUDA-event time in cell + gather + residual kernels */
   double t_krylov_ms;        /* cumulative CUDA-event time in the Krylov solve */
   double last_spmv_ms;       /* mean J*v kernel time of the last lvpp_time_spmv call */
+  double spmv_sampled_ms;    /* cumulative CUDA-event time of the J*v launches sampled inside Krylov solves */
+  int64_t spmv_samples;      /* number of sampled J*v launches (one per convergence poll) */
 } lvpp_stats;
 
 const char* lvpp_last_error(void);
@@ -184,6 +186,9 @@ int lvpp_newton_solve_host(lvpp_handle h, double* h_x, const lvpp_newton_opts* o
 int lvpp_set_previous_host(lvpp_handle h, const double* h_xk);
 
 /* ---- measurement helpers ---- */
+/* CUDA events on the handle's stream: start, then stop returns the elapsed device time in ms */
+int lvpp_timer_start(lvpp_handle h);
+int lvpp_timer_stop(lvpp_handle h, double* h_ms);
 /* runs the J*v kernel `reps` times on the handle's stream between CUDA events and returns the mean
  * kernel time in ms; flush_l2 != 0 writes a >L2 scratch buffer between repetitions (untimed). */
 int lvpp_time_spmv(lvpp_handle h, const double* d_v, double* d_y, int32_t reps, int32_t flush_l2,

@@ -140,20 +140,26 @@ class ObstacleOracle:
         pkq = pkl @ phi.T
         gu = np.einsum("ca,cqag->cqg", ul, self.gphi)
         ws = w[None, :] * s[:, None]  # [C, nq]
-        Fu = alpha * np.einsum("cq,cqg,cqag->ca", ws, gu, self.gphi)
+        Fu = alpha * np.einsum("cqg,cqag->ca", ws[:, :, None] * gu, self.gphi)
         Fu += np.einsum("cq,qa->ca", ws * (pq - alpha * self.f - pkq), phi)
         Fp = np.einsum("cq,qa->ca", ws * (uq - np.exp(pq) - self.phi_q), phi)
         return np.concatenate([Fu, Fp], axis=1)
 
-    def element_jacobian(self, x, alpha):
-        """tabulate_tensor of J = derivative(F, sol) (obstacle_pg.py:125): [C, 2*nld, 2*nld]."""
-        _, pl = self._local(x)
-        phi, w, s = self.phi_tab, self.qwts, self.scale
+    def element_jacobian(self, x, alpha, cells=None):
+        """tabulate_tensor of J = derivative(F, sol) (obstacle_pg.py:125): [C, 2*nld, 2*nld]
+        (``cells``: optional subset, as apply_lifting only visits cells with a Dirichlet dof)."""
+        sel = slice(None) if cells is None else cells
+        pl = x[self.dof_psi[self.cell_nodes[sel]]]
+        phi, w, s = self.phi_tab, self.qwts, self.scale[sel]
+        gphi = self.gphi[sel]
         pq = pl @ phi.T
         ws = w[None, :] * s[:, None]
-        K = np.einsum("cq,cqag,cqbg->cab", ws, self.gphi, self.gphi)
-        M = np.einsum("cq,qa,qb->cab", ws, phi, phi)
-        D = np.einsum("cq,qa,qb->cab", ws * np.exp(pq), phi, phi)
+        # the three quadrature sums  sum_q ws[c,q] * (.)_a(q) * (.)_b(q)  written as batched matmuls
+        nc, nq, na, ng = gphi.shape
+        G = np.transpose(gphi, (0, 1, 3, 2)).reshape(nc, nq * ng, na)  # [(q,g), a]
+        K = np.matmul(np.transpose(G * np.repeat(ws, ng, axis=1)[:, :, None], (0, 2, 1)), G)
+        M = np.matmul(np.transpose(ws[:, :, None] * phi[None], (0, 2, 1)), phi)
+        D = np.matmul(np.transpose((ws * np.exp(pq))[:, :, None] * phi[None], (0, 2, 1)), phi)
         n = self.nld
         A = np.empty((K.shape[0], 2 * n, 2 * n))
         A[:, :n, :n] = alpha * K
@@ -168,10 +174,10 @@ class ObstacleOracle:
         Fe = self.element_residual(x, xk, alpha)
         b = np.bincount(self.cell_dofs.ravel(), weights=Fe.ravel(), minlength=self.num_rows)
         # apply_lifting(b, [a], bcs, x0=[x], scale=-1):  b -= scale * A_e (g - x0) over BC columns
-        Ae = self.element_jacobian(x, alpha)
-        gmx = np.where(self.is_bc, self.bc_values - x, 0.0)[self.cell_dofs]  # [C, n]
-        touched = self.is_bc[self.cell_dofs].any(axis=1)
-        lift = np.einsum("cij,cj->ci", Ae[touched], gmx[touched])
+        touched = np.flatnonzero(self.is_bc[self.cell_dofs].any(axis=1))
+        Ae = self.element_jacobian(x, alpha, cells=touched)
+        gmx = np.where(self.is_bc, self.bc_values - x, 0.0)[self.cell_dofs[touched]]  # [Ct, n]
+        lift = np.einsum("cij,cj->ci", Ae, gmx)
         b += np.bincount(self.cell_dofs[touched].ravel(), weights=lift.ravel(), minlength=self.num_rows)
         # set_bc(b, bcs, x0=x, scale=-1): b[d] = -(g[d] - x[d])
         b[self.bc_dofs] = -(self.bc_values[self.bc_dofs] - x[self.bc_dofs])

@@ -97,6 +97,8 @@ class Stats(C.Structure):
         ("t_assembly_ms", C.c_double),
         ("t_krylov_ms", C.c_double),
         ("last_spmv_ms", C.c_double),
+        ("spmv_sampled_ms", C.c_double),
+        ("spmv_samples", C.c_int64),
     ]
 
     def as_dict(self):
@@ -128,6 +130,8 @@ SIGNATURES = {
     "lvpp_observables": (C.c_int, [H, VP, c_double_p]),
     "lvpp_newton_solve_host": (C.c_int, [H, c_double_p, C.POINTER(NewtonOpts), c_int32_p, c_int32_p, c_double_p, c_int32_p]),
     "lvpp_set_previous_host": (C.c_int, [H, c_double_p]),
+    "lvpp_timer_start": (C.c_int, [H]),
+    "lvpp_timer_stop": (C.c_int, [H, c_double_p]),
     "lvpp_time_spmv": (C.c_int, [H, VP, VP, C.c_int32, C.c_int32, c_double_p]),
     "lvpp_time_assembly": (C.c_int, [H, VP, VP, C.c_int32, c_double_p, c_double_p, c_double_p]),
     "lvpp_comm_unique_id": (C.c_int, [c_uint8_p]),

@@ -178,7 +178,9 @@ int lvpp_minres(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_ne
     for (int k = 0; k < check_every; ++k) {
       // 1. Az = J (z1 / gamma1), partial delta
       if (h->nranks > 1) CKR(lvpp_halo_forward_impl(h, (double*)z1));
+      if (k == 0) CK(cudaEventRecord(h->evs0, h->stream));  // sample one J*v launch per poll
       CKR(lvpp_apply_jacobian(h, (const double*)z1, h->Az, &h->scal->inv_gamma1, h->partials, &h->scal->conv));
+      if (k == 0) CK(cudaEventRecord(h->evs1, h->stream));
       CKR(lvpp_reduce_partials(h, 1, h->scal->red));
       LAUNCH(h, k_minres_scal1, 1, 1, 0, h->scal);
       // 2. Lanczos vector + preconditioner, partial gamma2^2
@@ -197,6 +199,12 @@ int lvpp_minres(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_ne
     }
     CK(cudaMemcpyAsync(h->scal_host, h->scal, sizeof(KryScal), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    {
+      float sms = 0.f;
+      CK(cudaEventElapsedTime(&sms, h->evs0, h->evs1));
+      h->spmv_sampled_ms += sms;
+      h->spmv_samples++;
+    }
     done = h->scal_host->conv != 0 || launched >= maxit + check_every;
   }
   CK(cudaEventRecord(h->ev1, h->stream));

@@ -107,7 +107,9 @@ struct lvpp_problem {
   // stats
   int64_t krylov_its = 0, newton_steps = 0, residual_evals = 0;
   double t_assembly_ms = 0.0, t_krylov_ms = 0.0, last_spmv_ms = 0.0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs0 = nullptr, evs1 = nullptr, evt0 = nullptr, evt1 = nullptr;
+  double spmv_sampled_ms = 0.0;
+  int64_t spmv_samples = 0;
   // communication
   int rank = 0, nranks = 1;
   void* nccl_comm = nullptr;

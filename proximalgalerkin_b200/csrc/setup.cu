@@ -327,6 +327,10 @@ extern "C" int lvpp_create(const lvpp_obstacle_desc* d, lvpp_handle* out) {
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
+    CK(cudaEventCreate(&h->evs0));
+    CK(cudaEventCreate(&h->evs1));
+    CK(cudaEventCreate(&h->evt0));
+    CK(cudaEventCreate(&h->evt1));
     h->tdim = d->tdim; h->nld = d->nld; h->nq = d->nq;
     h->nsym = d->nld * (d->nld + 1) / 2;
     h->V = d->num_nodes; h->Vown = d->num_owned; h->C = d->num_cells; h->Cown = d->num_owned_cells;
@@ -427,6 +431,10 @@ extern "C" int lvpp_destroy(lvpp_handle h) {
   if (h->red_host) cudaFreeHost(h->red_host);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->evs0) cudaEventDestroy(h->evs0);
+  if (h->evs1) cudaEventDestroy(h->evs1);
+  if (h->evt0) cudaEventDestroy(h->evt0);
+  if (h->evt1) cudaEventDestroy(h->evt1);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return LVPP_OK;
@@ -447,6 +455,25 @@ extern "C" int lvpp_get_stats(lvpp_handle h, lvpp_stats* s) {
   s->t_assembly_ms = h->t_assembly_ms;
   s->t_krylov_ms = h->t_krylov_ms;
   s->last_spmv_ms = h->last_spmv_ms;
+  s->spmv_sampled_ms = h->spmv_sampled_ms;
+  s->spmv_samples = h->spmv_samples;
+  return LVPP_OK;
+}
+
+extern "C" int lvpp_timer_start(lvpp_handle h) {
+  if (!h) { lvpp_set_error("null handle"); return LVPP_E_INVALID; }
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventRecord(h->evt0, h->stream));
+  return LVPP_OK;
+}
+extern "C" int lvpp_timer_stop(lvpp_handle h, double* h_ms) {
+  if (!h || !h_ms) { lvpp_set_error("null argument"); return LVPP_E_INVALID; }
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventRecord(h->evt1, h->stream));
+  CK(cudaEventSynchronize(h->evt1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, h->evt0, h->evt1));
+  *h_ms = ms;
   return LVPP_OK;
 }
 

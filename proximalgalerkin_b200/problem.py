@@ -311,6 +311,14 @@ class DeviceProblem:
         _capi.check(self.lib.lvpp_observables(self.h, x.ptr, out))
         return np.array(out[:])
 
+    def timer_start(self):
+        _capi.check(self.lib.lvpp_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        _capi.check(self.lib.lvpp_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
     def time_spmv(self, v: DeviceVector, y: DeviceVector, reps=20, flush_l2=False):
         _torch().cuda.current_stream().synchronize()
         ms = C.c_double()
