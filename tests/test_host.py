@@ -1,0 +1,120 @@
+"""Host-side logic of the product (no GPU): meshes and slab partitions, spaces, tables, option
+parsing, the alpha schedule, and that the product never touches the oracle."""
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import proximalgalerkin_b200 as lvpp
+from oracle import elements as oelem
+from oracle import mesh as omesh
+from oracle import obstacle as oobs
+from oracle import quadrature as oquad
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_meshes_match_oracle_numbering():
+    m, o = lvpp.mesh.create_box(3, 4, 5), omesh.box_kuhn(3, 4, 5)
+    assert np.array_equal(m.cells, o.cells) and np.allclose(m.coords, o.coords, rtol=0, atol=1e-15)
+    assert np.array_equal(m.boundary_vertices, omesh.boundary_vertices(o))
+    m, o = lvpp.mesh.create_rectangle(6, 5), omesh.rectangle(6, 5)
+    assert np.array_equal(m.cells, o.cells) and np.allclose(m.coords, o.coords, rtol=0, atol=1e-15)
+    assert np.array_equal(m.boundary_vertices, omesh.boundary_vertices(o))
+    g = lvpp.mesh.from_arrays(o.coords, o.cells)
+    assert np.array_equal(g.boundary_vertices, omesh.boundary_vertices(o))
+
+
+@pytest.mark.parametrize("make,shape", [(lvpp.mesh.create_box, (4, 3, 9)), (lvpp.mesh.create_rectangle, (5, 11))])
+@pytest.mark.parametrize("nranks", [2, 3, 4])
+def test_slab_partition(make, shape, nranks):
+    whole = make(*shape)
+    parts = [make(*shape, rank=r, nranks=nranks) for r in range(nranks)]
+    # owned vertices partition the global numbering; coordinates agree with the global mesh
+    owned = np.concatenate([p.global_vertex[: p.num_owned_vertices] for p in parts])
+    assert np.array_equal(np.sort(owned), np.arange(whole.num_vertices))
+    for p in parts:
+        assert np.allclose(p.coords, whole.coords[p.global_vertex], rtol=0, atol=1e-15)
+        assert np.array_equal(np.sort(p.global_vertex[p.boundary_vertices]),
+                              np.intersect1d(whole.boundary_vertices, p.global_vertex))
+    # owned cells partition the global cells (as global vertex tuples)
+    gc = np.concatenate([p.global_vertex[p.cells[: p.num_owned_cells]] for p in parts])
+    assert np.array_equal(np.sort(gc.view([("", gc.dtype)] * gc.shape[1]).ravel()),
+                          np.sort(whole.cells.astype(np.int64).view([("", np.int64)] * gc.shape[1]).ravel()))
+    # every cell incident to an owned vertex is present locally
+    for p in parts:
+        own_g = set(p.global_vertex[: p.num_owned_vertices].tolist())
+        need = {tuple(c) for c in whole.cells.astype(np.int64).tolist() if own_g.intersection(c)}
+        have = {tuple(c) for c in p.global_vertex[p.cells].tolist()}
+        assert need <= have
+    # halo lists: what r sends to s is what s receives from r, in the same order
+    for p in parts:
+        for nb, send in zip(p.halo.neighbors, p.halo.send):
+            q = parts[nb]
+            recv = q.halo.recv[q.halo.neighbors.index(p.rank)]
+            assert np.all(send < p.num_owned_vertices) and np.all(recv >= q.num_owned_vertices)
+            assert np.array_equal(p.global_vertex[send], q.global_vertex[recv])
+        ghosts = np.concatenate(p.halo.recv) if p.halo.recv else np.zeros(0, dtype=np.int32)
+        assert np.array_equal(np.sort(ghosts), np.arange(p.num_owned_vertices, p.num_vertices))
+
+
+def test_tables_and_spaces_match_oracle():
+    for cell, tdim in (("triangle", 2), ("tetrahedron", 3)):
+        for deg in (1, 2, 4, 6, 9):
+            p, w = lvpp.quadrature.make_quadrature(cell, deg)
+            po, wo = oquad.make_quadrature(cell, deg)
+            assert np.allclose(p, po, rtol=0, atol=1e-15) and np.allclose(w, wo, rtol=0, atol=1e-16)
+        for degree in (1, 2):
+            phi, dphi = lvpp.fem.tabulate_lagrange(degree, p)
+            phio, dphio = oelem.tabulate(degree, p)
+            assert np.array_equal(phi, phio) and np.array_equal(dphi, dphio)
+    msh, om = lvpp.mesh.create_box(3, 3, 2), omesh.box_kuhn(3, 3, 2)
+    for degree in (1, 2):
+        V = lvpp.fem.functionspace(msh, ("Lagrange", degree))
+        orc = oobs.ObstacleOracle(om, degree=degree)
+        assert np.array_equal(V.cell_nodes, orc.cell_nodes)
+        assert np.allclose(V.node_coords, orc.node_coords)
+        assert np.array_equal(np.sort(V.boundary_nodes), orc.bc_nodes)
+        dofs = lvpp.fem.locate_dofs_boundary(V.sub(0))
+        assert np.array_equal(np.sort(dofs), orc.bc_dofs)
+    phi = lvpp.fem.QuadratureFunction(V)
+    phi.interpolate(lvpp.fem.phi_set)
+    assert np.allclose(phi.values, orc.phi_q, rtol=1e-15, atol=1e-17)
+
+
+def test_alpha_update_known_answers():
+    expect = [1.0, 1.0, 1.4900343193257237, 2.439200639104808, 5.349445965312164, 16.387223352344883,
+              84.95478289516922, 100.0, 100.0]
+    a, ak, got = 1.0, 1, []
+    for k in range(9):
+        a, ak = lvpp.obstacle_pg.alpha_update("double_exponential", k, a, ak, 1e2)
+        got.append(a)
+    assert np.allclose(got, expect, rtol=1e-14)
+    assert ak > 100.0  # alpha_k is stored before clamping (obstacle_pg.py:182-183)
+
+
+def test_option_parsing():
+    o = lvpp.newton_options(lvpp.obstacle_pg.PETSC_OPTIONS)
+    assert (o.snes_rtol, o.snes_max_it, o.snes_atol, o.snes_stol, o.snes_divtol) == (1e-6, 100, 1e-50, 1e-8, 1e4)
+    assert o.ksp_rtol == 1e-12
+    o = lvpp.newton_options({})
+    assert (o.snes_rtol, o.snes_max_it) == (1e-8, 50)  # PETSc defaults
+    for bad in ({"snes_linesearch_type": "bt"}, {"ksp_type": "gmres"}, {"pc_type": "hypre"}, {"snes_type": "vinewtonssls"}):
+        with pytest.raises(NotImplementedError):
+            lvpp.newton_options(bad)
+
+
+def test_no_cpu_fallback_and_no_oracle_in_product():
+    import torch
+
+    for path in (ROOT / "proximalgalerkin_b200").rglob("*"):
+        if path.suffix in (".py", ".cu", ".cuh", ".h"):
+            text = path.read_text()
+            assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), path
+            assert "/root/reference" not in text, path
+    if not torch.cuda.is_available():
+        msh = lvpp.mesh.create_rectangle(4, 4)
+        s = lvpp.obstacle_pg.setup(msh)
+        with pytest.raises(lvpp._capi.LvppError):
+            s["problem"].solve()
