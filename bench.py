@@ -10,7 +10,7 @@ iterate with the reference's CI parameters (double-exponential alpha, alpha_max 
 SNES rtol 1e-6).  Warm-up steps are the first W Newton steps of that solve; the K timed steps
 continue it.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--n 215] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size 215] [--impl b200|reference]
 
 --impl reference times the CPU restatement of the reference algorithm (oracle/: numpy assembly +
 SuperLU in place of dolfinx + MUMPS; the real stack is not installable here) on a bounded sample.
@@ -320,13 +320,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n", type=int, default=215, help="cubes per axis per GPU")
-    ap.add_argument("--n-cpu", dest="n_cpu", type=int, default=16, help="cubes per axis of the CPU sample")
+    ap.add_argument("--size", dest="n", type=int, default=215, help="cubes per axis per GPU")
+    ap.add_argument("--cpu-size", dest="n_cpu", type=int, default=16, help="cubes per axis of the CPU sample")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ksp-rtol", dest="ksp_rtol", type=float, default=1e-12)
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-aux", action="store_true")
+    ap.add_argument("--skip-e2e", dest="no_e2e", action="store_true")
+    ap.add_argument("--skip-cpu", dest="no_cpu", action="store_true")
+    ap.add_argument("--skip-aux", dest="no_aux", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -59,7 +59,9 @@ typedef struct lvpp_problem* lvpp_handle;
 /* Preconditioner for the saddle-point Krylov solve (recipe of examples/09_eikonal/ex40.cpp:261-274:
  * diagonal on the (0,0) block, diag Schur approximation D + M diag(A)^-1 M on the (1,1) block). */
 #define LVPP_PC_JACOBI 0
-#define LVPP_PC_CHEBYSHEV 1 /* Chebyshev-Jacobi polynomial of degree pc_degree on the (0,0) block */
+#define LVPP_PC_CHEBYSHEV 1 /* reserved */
+/* monolithic aggregation multigrid (node-block Jacobi smoother) preconditioning restarted GMRES */
+#define LVPP_PC_MG 2
 
 /* Replaces, for the obstacle forms of obstacle_pg.py:68-125: fem.functionspace(mixed P_p x P_p)
  * (:68-70), the Dirichlet data (:76-83), the quadrature-space obstacle Function (:106-111), the
@@ -106,7 +108,7 @@ typedef struct lvpp_newton_opts {
   double ksp_atol;
   int32_t ksp_max_it;
   int32_t pc_type;    /* LVPP_PC_* */
-  int32_t pc_degree;  /* Chebyshev degree */
+  int32_t pc_degree;  /* LVPP_PC_MG: smoothing sweeps before and after the coarse correction (0 = 2) */
 } lvpp_newton_opts;
 
 typedef struct lvpp_stats {

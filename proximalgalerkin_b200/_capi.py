@@ -13,7 +13,7 @@ LIB_PATH = Path(__file__).resolve().parent / "lib" / "liblvpp_b200.so"
 OK = 0
 E_INVALID, E_CUDA, E_CAPACITY, E_COMM, E_NOGPU = -1, -2, -3, -4, -5
 OBSTACLE_ARRAY, OBSTACLE_PHI_SET = 0, 1
-PC_JACOBI, PC_CHEBYSHEV = 0, 1
+PC_JACOBI, PC_CHEBYSHEV, PC_MG = 0, 1, 2
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)

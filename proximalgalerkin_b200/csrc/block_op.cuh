@@ -1,0 +1,115 @@
+// The 2x2-block operator on the sliced-ELL node pattern; one thread per owned node (= two rows).
+// Shared by assembly.cu (J*v, residual), krylov.cu (MINRES) and multigrid.cu (smoother, residual on
+// every level of the hierarchy: coarse levels have exactly the fine level's structure).
+//
+//   MODE 0 (J*v):  y_u = alpha K v_u + M v_psi,  y_psi = M v_u - D v_psi  with Dirichlet rows/columns
+//                  of u replaced by the identity (assemble_matrix with bcs, src/lvpp/problem.py:76),
+//                  optional input scaling *inv_scale and fused partial sum of (scaled v) . y.
+//                  Epilogue `epi`:  EPI_NONE   y = J v
+//                                   EPI_RESID  y = b - J v
+//                                   EPI_JACOBI y = v + omega * Binv (b - J v)   (damped node-block Jacobi)
+//   MODE 1 (F):    residual of obstacle_pg.py:116-124 with apply_lifting(x0 = x, scale -1) and
+//                  set_bc(x, -1) (src/lvpp/problem.py:59-67): the linear part is evaluated at x with
+//                  its Dirichlet entries replaced by g, Dirichlet rows are x - g; fused partial ||F||^2.
+#pragma once
+#include "lvpp_internal.cuh"
+
+enum { EPI_NONE = 0, EPI_RESID = 1, EPI_JACOBI = 2 };
+
+struct OpArgs {
+  int64_t Vown;
+  const int64_t* slice_ptr;
+  const uint32_t* col;
+  const double *K, *M, *D;
+  const uint8_t* bc_flag;
+  const double* bc_val;
+  double alpha;
+  const double2* v;    // MODE 0: input; MODE 1: x
+  const double2* xk;   // MODE 1
+  const double *bobs, *fvec;
+  double f;
+  const double* inv_scale;
+  const int* skip_flag;  // MODE 0: device flag, non-zero = Krylov solve already converged, do nothing
+  double2* y;
+  double* partials;    // [gridDim] or null
+  // epilogue (MODE 0)
+  int epi;
+  const double2* b;
+  const double* binv;  // [Vown * 4]
+  double omega;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_block_op(OpArgs p) {
+  __shared__ double s_red[32];
+  double part = 0.0;
+  if (MODE == 0 && p.skip_flag && *p.skip_flag) return;
+  const double sc = (MODE == 0 && p.inv_scale) ? *p.inv_scale : 1.0;
+  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x; i0 < p.Vown; i0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = i0 + threadIdx.x;
+    if (i < p.Vown) {
+      const int64_t s = i >> 5;
+      const int64_t b0 = p.slice_ptr[s];
+      const int w = (int)((p.slice_ptr[s + 1] - b0) >> 5);
+      const int64_t base = b0 + (i & 31);
+      double au = 0.0, ap = 0.0;
+#pragma unroll 4
+      for (int k = 0; k < w; ++k) {
+        const int64_t idx = base + (int64_t)k * LVPP_SLICE;
+        const uint32_t c = p.col[idx];
+        const double kv = p.K[idx], mv = p.M[idx], dv = p.D[idx];
+        const uint32_t j = c & ~LVPP_COL_BC;
+        double2 vj = __ldg(&p.v[j]);
+        if (MODE == 0) {
+          if (c & LVPP_COL_BC) vj.x = 0.0;
+          au += p.alpha * kv * vj.x + mv * vj.y;
+          ap += mv * vj.x - dv * vj.y;
+        } else {
+          if (c & LVPP_COL_BC) vj.x = p.bc_val[j];
+          const double pk = __ldg(&p.xk[j]).y;
+          au += p.alpha * kv * vj.x + mv * (vj.y - pk);
+          ap += mv * vj.x - dv;
+        }
+      }
+      const double2 vi = p.v[i];
+      const bool isbc = p.bc_flag[i] != 0;
+      double2 out;
+      if (MODE == 0) {
+        out.x = isbc ? vi.x * sc : au * sc;
+        out.y = ap * sc;
+        part += (out.x * vi.x + out.y * vi.y) * sc;
+        if (p.epi != EPI_NONE) {
+          const double2 bi = p.b[i];
+          const double ru = bi.x - out.x, rp = bi.y - out.y;
+          if (p.epi == EPI_RESID) {
+            out.x = ru;
+            out.y = rp;
+          } else {
+            const double* B = p.binv + 4 * i;
+            out.x = vi.x + p.omega * (B[0] * ru + B[1] * rp);
+            out.y = vi.y + p.omega * (B[2] * ru + B[3] * rp);
+          }
+        }
+      } else {
+        out.x = isbc ? (vi.x - p.bc_val[i]) : (au - p.alpha * p.f * p.fvec[i]);
+        out.y = ap - p.bobs[i];
+        part += out.x * out.x + out.y * out.y;
+      }
+      p.y[i] = out;
+    }
+  }
+  if (p.partials) {
+    const double r = lvpp_block_sum<256>(part, s_red);
+    if (threadIdx.x == 0) p.partials[blockIdx.x] = r;
+  }
+}
+
+static inline OpArgs lvpp_level_op(const lvpp_problem* h, const MgLevel& L) {
+  OpArgs p;
+  p.Vown = L.Vown; p.slice_ptr = L.slice_ptr; p.col = L.col;
+  p.K = L.K; p.M = L.M; p.D = L.D; p.bc_flag = L.bc_flag; p.bc_val = nullptr;
+  p.alpha = h->alpha; p.v = nullptr; p.xk = nullptr; p.bobs = nullptr; p.fvec = nullptr;
+  p.f = 0.0; p.inv_scale = nullptr; p.skip_flag = nullptr; p.y = nullptr; p.partials = nullptr;
+  p.epi = EPI_NONE; p.b = nullptr; p.binv = nullptr; p.omega = 1.0;
+  return p;
+}

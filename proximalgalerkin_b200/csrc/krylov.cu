@@ -219,12 +219,22 @@ int lvpp_minres(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_ne
   return 0;
 }
 
+int lvpp_solve_linear(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_newton_opts* o, int32_t* its,
+                      int32_t* reason, double* rnorm) {
+  if (o->pc_type == LVPP_PC_MG) {
+    if (o->pc_degree > 0) h->mg_nsmooth = o->pc_degree;
+    CKR(lvpp_mg_update(h));
+    return lvpp_gmres_mg(h, d_rhs, d_y, o, its, reason, rnorm);
+  }
+  CKR(lvpp_build_preconditioner(h, o));
+  return lvpp_minres(h, d_rhs, d_y, o, its, reason, rnorm);
+}
+
 extern "C" int lvpp_linear_solve(lvpp_handle h, const double* d_rhs, double* d_y, const lvpp_newton_opts* opts,
                                  int32_t* its, int32_t* reason, double* h_rnorm) {
   if (!h || !d_rhs || !d_y || !opts) { lvpp_set_error("null argument"); return LVPP_E_INVALID; }
   CK(cudaSetDevice(h->device));
   if (!h->jac_valid) { lvpp_set_error("no Jacobian assembled yet"); return LVPP_E_INVALID; }
-  CKR(lvpp_build_preconditioner(h, opts));
-  CKR(lvpp_minres(h, d_rhs, d_y, opts, its, reason, h_rnorm));
+  CKR(lvpp_solve_linear(h, d_rhs, d_y, opts, its, reason, h_rnorm));
   return LVPP_OK;
 }

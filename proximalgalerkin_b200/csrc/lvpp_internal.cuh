@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <utility>
@@ -54,6 +55,42 @@ struct KryScal {
   double rtol, atol;
   double red[8];          // reduction results (allreduced across ranks)
   int conv, skip, its, reason, maxit;
+};
+
+// halo description of one level (owned nodes first, ghosts last)
+struct LevelHalo {
+  int num_neighbors = 0;
+  std::vector<int32_t> neighbor_ranks;
+  std::vector<int64_t> send_ptr, recv_ptr;
+  int32_t* send_nodes = nullptr;  // device
+  int32_t* recv_nodes = nullptr;  // device
+  double* send_buf = nullptr;     // device [2 * nsend]
+  double* recv_buf = nullptr;     // device [2 * nrecv]
+};
+
+// one level of the aggregation multigrid hierarchy; level 0 aliases the fine operator
+struct MgLevel {
+  int64_t V = 0, Vown = 0;       // nodes owned + ghost, owned
+  int64_t nslices = 0, slots = 0, nnz = 0;
+  int64_t* slice_ptr = nullptr;
+  uint32_t* col = nullptr;
+  int32_t* rowlen = nullptr;
+  uint8_t* diag_k = nullptr;
+  double *K = nullptr, *M = nullptr, *D = nullptr;
+  uint8_t* bc_flag = nullptr;    // [V] u dof of the node is inactive (Dirichlet / all-Dirichlet aggregate)
+  int32_t* box = nullptr;        // [Vown * 3] integer box coordinates used by the coordinate aggregation
+  // transfer to the next coarser level
+  int32_t* agg = nullptr;        // [V] coarse node of every node
+  int64_t* agg_ptr = nullptr;    // [Vc_own + 1]
+  int32_t* agg_members = nullptr;// [Vown] owned nodes grouped by coarse node
+  int64_t* gal_ptr = nullptr;    // [nnz_c + 1] segments of gal_src per coarse entry (CSR order)
+  uint32_t* gal_src = nullptr;   // [slots] fine slots grouped by coarse entry, ascending inside a group
+  int64_t* gal_dst = nullptr;    // [nnz_c] SELL slot of the coarse entry
+  // smoother / work vectors [2V]
+  double* binv = nullptr;        // [Vown * 4] inverse of the 2x2 node block, row-major
+  double *b = nullptr, *x = nullptr, *t = nullptr;
+  LevelHalo halo;
+  bool replicated = false;       // multi-GPU: level holds the whole (all ranks') coarse problem
 };
 
 struct lvpp_problem {
@@ -121,6 +158,21 @@ struct lvpp_problem {
   double* send_buf = nullptr;     // device [2 * nsend]
   double* recv_buf = nullptr;     // device [2 * nrecv]
   int64_t global_rows = 0;
+  // multigrid hierarchy + GMRES workspace (built lazily by lvpp_mg_setup)
+  std::vector<MgLevel> levels;
+  bool mg_ready = false;
+  double h0 = 0.0;                // node spacing used by the coordinate aggregation
+  double xmin[3] = {0, 0, 0};
+  int mg_nsmooth = 2;
+  double mg_omega = 0.7, mg_over = 1.0;
+  double* coarse_lu = nullptr;    // dense LU of the coarsest operator [nc * nc]
+  int32_t* coarse_piv = nullptr;
+  int coarse_n = 0;
+  double* gm_V = nullptr;         // GMRES basis [(restart + 1) * 2V]
+  int gm_restart = 0;
+  double* gm_h = nullptr;         // device [restart + 2]
+  double* gm_h_host = nullptr;    // pinned
+  int64_t vcycles = 0;
 };
 
 template <class T>
@@ -191,4 +243,11 @@ int lvpp_halo_forward_impl(lvpp_problem* h, double* d_v);            // comm.cu
 int lvpp_minres(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_newton_opts* o,
                 int32_t* its, int32_t* reason, double* rnorm);       // krylov.cu
 int lvpp_build_preconditioner(lvpp_problem* h, const lvpp_newton_opts* o);  // krylov.cu
-void lvpp_comm_destroy(lvpp_problem* h);                             // comm.cu
+void lvpp_comm_destroy(lvpp_problem* h);
+int lvpp_mg_setup(lvpp_problem* h);                                  // multigrid.cu
+int lvpp_mg_update(lvpp_problem* h);                                 // multigrid.cu
+int lvpp_mg_vcycle(lvpp_problem* h, const double* b_in, double** z_out);  // multigrid.cu
+int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_newton_opts* o, int32_t* its,
+                  int32_t* reason, double* rnorm);                   // multigrid.cu
+int lvpp_solve_linear(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_newton_opts* o, int32_t* its,
+                      int32_t* reason, double* rnorm);               // krylov.cu: dispatch on pc_type                             // comm.cu

@@ -1,0 +1,844 @@
+// Monolithic aggregation multigrid for the saddle-point Newton system and the GMRES that it
+// preconditions ("block-preconditioned MINRES/GMRES with a Jacobi ... smoother", BASELINE.json).
+//
+// J = [[alpha K, M], [M, -D(psi)]] is symmetric quasi-definite with one scalar node pattern and a 2x2
+// block per entry.  Block-diagonal preconditioners (the ex40.cpp:261-274 recipe used by the MINRES
+// path in krylov.cu) need O(1/h) iterations here because the diagonal Schur approximation is poor on
+// the contact set.  Instead both fields are coarsened together:
+//   * aggregates = boxes of 2^d neighbouring nodes found from the node coordinates (Dirichlet nodes
+//     are aggregated separately, so a coarse node is either free or Dirichlet and every level has
+//     exactly the fine level's structure: same kernels, same masks);
+//   * prolongation = piecewise constant per field; Galerkin coarse operators K_c, M_c, D_c are sums of
+//     fine entries through a precomputed, sorted (deterministic, atomic-free) slot map; only D_c is
+//     recomputed per Newton step;
+//   * smoother = damped node-block Jacobi: the 2x2 node blocks [[alpha K_ii, M_ii], [M_ii, -D_ii]]
+//     are inverted exactly, which locally eliminates psi (eigenvalues of Binv J are real, in (0, 2]);
+//   * coarsest level: explicit dense inverse (Gauss-Jordan with partial pivoting, one CTA).
+// The V-cycle is not SPD, so the Krylov method is right-preconditioned restarted GMRES (classical
+// Gram-Schmidt with selective re-orthogonalisation; Hessenberg/Givens on the host, two small D2H
+// reads per iteration; all reductions deterministic).
+#include <cub/cub.cuh>
+
+#include <cmath>
+
+#include "block_op.cuh"
+#include "lvpp_internal.cuh"
+
+#define MG_MAX_LEVELS 14
+#define MG_COARSE_TARGET 96    // stop coarsening at <= this many coarse nodes
+#define MG_COARSE_MAX 384      // dense inverse limit (unknowns = 2 * nodes)
+#define GM_CHUNK 8
+
+// ------------------------------------------------------------------------------------------------
+// setup kernels
+__global__ void k_box0(int64_t Vown, int tdim, const double* __restrict__ coords, double x0, double y0,
+                       double z0, double inv_h, int32_t* __restrict__ box) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vown; i += (int64_t)gridDim.x * blockDim.x) {
+    const double o[3] = {x0, y0, z0};
+    for (int d = 0; d < 3; ++d) {
+      int32_t b = 0;
+      if (d < tdim) {
+        const double q = (coords[i * tdim + d] - o[d]) * inv_h + 0.25;
+        b = q < 0 ? 0 : (q > 1048574.0 ? 1048574 : (int32_t)q);
+      }
+      box[i * 3 + d] = b;
+    }
+  }
+}
+
+__global__ void k_agg_keys(int64_t Vown, const int32_t* __restrict__ box, const uint8_t* __restrict__ bc,
+                           uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vown; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t bx = (uint64_t)(box[i * 3 + 0] >> 1), by = (uint64_t)(box[i * 3 + 1] >> 1),
+                   bz = (uint64_t)(box[i * 3 + 2] >> 1);
+    keys[i] = ((uint64_t)(bc[i] ? 1 : 0) << 62) | (bz << 40) | (by << 20) | bx;
+    vals[i] = (uint32_t)i;
+  }
+}
+
+__global__ void k_heads(int64_t n, const uint64_t* __restrict__ skeys, int64_t* __restrict__ head) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
+    head[p] = (p == 0 || skeys[p] != skeys[p - 1]) ? 1 : 0;
+}
+
+// after the inclusive scan of head: id[p] = scan[p] - 1
+__global__ void k_agg_fill(int64_t Vown, const uint64_t* __restrict__ skeys, const uint32_t* __restrict__ sidx,
+                           const int64_t* __restrict__ scan, int32_t* __restrict__ agg,
+                           int32_t* __restrict__ members, int64_t* __restrict__ agg_ptr,
+                           int32_t* __restrict__ cbox, uint8_t* __restrict__ cbc) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < Vown; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t id = scan[p] - 1;
+    agg[sidx[p]] = (int32_t)id;
+    members[p] = (int32_t)sidx[p];
+    if (p == 0 || skeys[p] != skeys[p - 1]) {
+      agg_ptr[id] = p;
+      const uint64_t k = skeys[p];
+      cbox[id * 3 + 0] = (int32_t)(k & 0xfffff);
+      cbox[id * 3 + 1] = (int32_t)((k >> 20) & 0xfffff);
+      cbox[id * 3 + 2] = (int32_t)((k >> 40) & 0xfffff);
+      cbc[id] = (uint8_t)((k >> 62) & 1);
+    }
+    if (p == Vown - 1) agg_ptr[id + 1] = Vown;
+  }
+}
+
+// key of every stored slot of the fine level: (coarse row << 32) | coarse column
+__global__ void k_gal_keys(int64_t Vown, const int64_t* __restrict__ slice_ptr, const uint32_t* __restrict__ col,
+                           const int32_t* __restrict__ agg, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vown; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b0 = slice_ptr[i >> 5];
+    const int w = (int)((slice_ptr[(i >> 5) + 1] - b0) >> 5);
+    const uint64_t I = (uint64_t)agg[i];
+    for (int k = 0; k < w; ++k) {
+      const int64_t s = b0 + (i & 31) + (int64_t)k * LVPP_SLICE;
+      const uint32_t j = col[s] & ~LVPP_COL_BC;
+      keys[s] = (I << 32) | (uint64_t)(uint32_t)agg[j];
+      vals[s] = (uint32_t)s;
+    }
+  }
+}
+
+__global__ void k_compact_heads(int64_t n, const uint64_t* __restrict__ skeys, const int64_t* __restrict__ scan,
+                                uint64_t* __restrict__ ukeys, int64_t* __restrict__ gal_ptr, int64_t nvalid) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nvalid; p += (int64_t)gridDim.x * blockDim.x)
+    if (p == 0 || skeys[p] != skeys[p - 1]) {
+      ukeys[scan[p] - 1] = skeys[p];
+      gal_ptr[scan[p] - 1] = p;
+    }
+}
+
+// first unique entry of every coarse row (lower bound of row << 32)
+__global__ void k_coarse_rowstart(int64_t Vc, int64_t nnzc, const uint64_t* __restrict__ ukeys,
+                                  int64_t* __restrict__ rowstart, int32_t* __restrict__ rowlen) {
+  for (int64_t I = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; I <= Vc; I += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t target = (uint64_t)I << 32;
+    int64_t lo = 0, hi = nnzc;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (ukeys[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    rowstart[I] = lo;
+  }
+}
+__global__ void k_coarse_rowlen(int64_t Vc, const int64_t* __restrict__ rowstart, int32_t* __restrict__ rowlen,
+                                int* __restrict__ err) {
+  for (int64_t I = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; I < Vc; I += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t len = rowstart[I + 1] - rowstart[I];
+    if (len > LVPP_MAX_ROW) atomicExch(err, 1);
+    rowlen[I] = (int32_t)len;
+  }
+}
+__global__ void k_slice_slots(int64_t nslices, int64_t Vc, const int32_t* __restrict__ rowlen, int64_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t s = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; s <= nslices;
+       s += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const int64_t i = s * LVPP_SLICE + lane;
+    int w = (s < nslices && i < Vc) ? rowlen[i] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
+    if (lane == 0) out[s] = (int64_t)w * LVPP_SLICE;
+  }
+}
+__global__ void k_coarse_cols(int64_t Vc, const int64_t* __restrict__ rowstart, const uint64_t* __restrict__ ukeys,
+                              const int64_t* __restrict__ slice_ptr, const uint8_t* __restrict__ cbc,
+                              uint32_t* __restrict__ col, uint8_t* __restrict__ diag_k, int64_t* __restrict__ gal_dst) {
+  for (int64_t I = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; I < Vc; I += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b0 = slice_ptr[I >> 5];
+    const int w = (int)((slice_ptr[(I >> 5) + 1] - b0) >> 5);
+    const int64_t u0 = rowstart[I];
+    const int len = (int)(rowstart[I + 1] - u0);
+    for (int k = 0; k < w; ++k) {
+      const int64_t s = b0 + (I & 31) + (int64_t)k * LVPP_SLICE;
+      if (k < len) {
+        const uint32_t J = (uint32_t)(ukeys[u0 + k] & 0xffffffffu);
+        col[s] = J | (cbc[J] ? LVPP_COL_BC : 0u);
+        gal_dst[u0 + k] = s;
+        if ((int64_t)J == I) diag_k[I] = (uint8_t)k;
+      } else {
+        col[s] = (uint32_t)I | (cbc[I] ? LVPP_COL_BC : 0u);
+      }
+    }
+  }
+}
+
+// Galerkin sums through the sorted slot map: Xc[dst[u]] = sum_{p in seg(u)} X[src[p]] (fixed order)
+__global__ void k_galerkin(int64_t nnzc, const int64_t* __restrict__ gal_ptr, const uint32_t* __restrict__ gal_src,
+                           const int64_t* __restrict__ gal_dst, int narr, const double* __restrict__ X0,
+                           const double* __restrict__ X1, double* __restrict__ Y0, double* __restrict__ Y1) {
+  for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < nnzc; u += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p1 = gal_ptr[u + 1];
+    double a0 = 0.0, a1 = 0.0;
+    for (int64_t p = gal_ptr[u]; p < p1; ++p) {
+      const uint32_t s = gal_src[p];
+      a0 += X0[s];
+      if (narr > 1) a1 += X1[s];
+    }
+    const int64_t d = gal_dst[u];
+    Y0[d] = a0;
+    if (narr > 1) Y1[d] = a1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// cycle kernels
+__global__ void k_build_binv(int64_t Vown, const int64_t* __restrict__ slice_ptr, const uint8_t* __restrict__ diag_k,
+                             const double* __restrict__ K, const double* __restrict__ M, const double* __restrict__ D,
+                             const uint8_t* __restrict__ bc, double alpha, double omega, double* __restrict__ binv) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vown; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t idx = slice_ptr[i >> 5] + (i & 31) + (int64_t)diag_k[i] * LVPP_SLICE;
+    const double a = alpha * K[idx], m = M[idx], d = D[idx];
+    double* B = binv + 4 * i;
+    if (bc[i]) {  // identity row for u (made exact under damping), psi decoupled from the masked column
+      B[0] = 1.0 / omega; B[1] = 0.0; B[2] = 0.0; B[3] = -1.0 / d;
+    } else {
+      const double idet = 1.0 / (-a * d - m * m);
+      B[0] = -d * idet; B[1] = -m * idet; B[2] = -m * idet; B[3] = a * idet;
+    }
+  }
+}
+
+__global__ void k_smooth_first(int64_t Vown, const double2* __restrict__ b, const double* __restrict__ binv,
+                               double omega, double2* __restrict__ x) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vown; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 r = b[i];
+    const double* B = binv + 4 * i;
+    x[i] = make_double2(omega * (B[0] * r.x + B[1] * r.y), omega * (B[2] * r.x + B[3] * r.y));
+  }
+}
+
+__global__ void k_restrict(int64_t Vc, const int64_t* __restrict__ agg_ptr, const int32_t* __restrict__ members,
+                           const double2* __restrict__ r, const uint8_t* __restrict__ cbc, double2* __restrict__ bc_out) {
+  for (int64_t I = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; I < Vc; I += (int64_t)gridDim.x * blockDim.x) {
+    double su = 0.0, sp = 0.0;
+    const int64_t p1 = agg_ptr[I + 1];
+    for (int64_t p = agg_ptr[I]; p < p1; ++p) {
+      const double2 v = r[members[p]];
+      su += v.x;
+      sp += v.y;
+    }
+    bc_out[I] = make_double2(cbc[I] ? 0.0 : su, sp);
+  }
+}
+
+__global__ void k_prolong_add(int64_t Vown, const int32_t* __restrict__ agg, const double2* __restrict__ xc,
+                              const uint8_t* __restrict__ bc, double over, double2* __restrict__ x) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vown; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 c = xc[agg[i]];
+    double2 v = x[i];
+    if (!bc[i]) v.x += over * c.x;
+    v.y += over * c.y;
+    x[i] = v;
+  }
+}
+
+// dense coarsest operator [n x 2n] = [J_c | I], n = 2 * Vc, Dirichlet masks applied
+__global__ void k_coarse_dense(int64_t Vc, const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ rowlen,
+                               const uint32_t* __restrict__ col, const double* __restrict__ K,
+                               const double* __restrict__ M, const double* __restrict__ D,
+                               const uint8_t* __restrict__ bc, double alpha, double* __restrict__ A) {
+  const int64_t n = 2 * Vc, ld = 2 * n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vc; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t base = slice_ptr[i >> 5] + (i & 31);
+    const bool rbc = bc[i] != 0;
+    const int len = rowlen[i];
+    for (int k = 0; k < len; ++k) {
+      const int64_t idx = base + (int64_t)k * LVPP_SLICE;
+      const uint32_t c = col[idx];
+      const bool cbc = (c & LVPP_COL_BC) != 0;
+      const int64_t j = c & ~LVPP_COL_BC;
+      double kuu = alpha * K[idx], kup = M[idx], kpu = M[idx], kpp = -D[idx];
+      if (rbc) { kuu = (j == i) ? 1.0 : 0.0; kup = 0.0; }
+      if (cbc) { if (!rbc) kuu = 0.0; kpu = 0.0; }
+      A[(2 * i) * ld + 2 * j] = kuu;
+      A[(2 * i) * ld + 2 * j + 1] = kup;
+      A[(2 * i + 1) * ld + 2 * j] = kpu;
+      A[(2 * i + 1) * ld + 2 * j + 1] = kpp;
+    }
+    A[(2 * i) * ld + n + 2 * i] = 1.0;
+    A[(2 * i + 1) * ld + n + 2 * i + 1] = 1.0;
+  }
+}
+
+// Gauss-Jordan with partial pivoting on [A | I] in one CTA; writes inv column-major: inv[c * n + r]
+__global__ void __launch_bounds__(1024) k_gauss_jordan(int n, double* __restrict__ A, double* __restrict__ inv,
+                                                        int* __restrict__ err) {
+  __shared__ double s_val[32];
+  __shared__ int s_idx[32];
+  __shared__ int s_piv;
+  const int ld = 2 * n, tid = threadIdx.x, nt = blockDim.x;
+  for (int k = 0; k < n; ++k) {
+    // pivot search in column k, rows k..n-1
+    double best = -1.0;
+    int bi = k;
+    for (int r = k + tid; r < n; r += nt) {
+      const double v = fabs(A[(int64_t)r * ld + k]);
+      if (v > best) { best = v; bi = r; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_down_sync(0xffffffffu, best, o);
+      const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { s_val[tid >> 5] = best; s_idx[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid < 32) {
+      best = tid < (nt >> 5) ? s_val[tid] : -1.0;
+      bi = tid < (nt >> 5) ? s_idx[tid] : n;
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, best, o);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if (tid == 0) {
+        s_piv = bi;
+        if (!(best > 0.0)) *err = 1;
+      }
+    }
+    __syncthreads();
+    const int p = s_piv;
+    if (p != k)
+      for (int c = k + tid; c < ld; c += nt) {
+        const double t = A[(int64_t)k * ld + c];
+        A[(int64_t)k * ld + c] = A[(int64_t)p * ld + c];
+        A[(int64_t)p * ld + c] = t;
+      }
+    __syncthreads();
+    const double ipiv = 1.0 / A[(int64_t)k * ld + k];
+    __syncthreads();
+    for (int c = k + tid; c < ld; c += nt) A[(int64_t)k * ld + c] *= ipiv;
+    __syncthreads();
+    // eliminate column k from all other rows (row swaps move the identity part: all columns > k)
+    const int c0 = k + 1, c1 = ld, ncol = c1 - c0;
+    for (int64_t e = tid; e < (int64_t)n * ncol; e += nt) {
+      const int r = (int)(e / ncol), c = c0 + (int)(e % ncol);
+      if (r == k) continue;
+      const double f = A[(int64_t)r * ld + k];
+      if (f != 0.0) A[(int64_t)r * ld + c] -= f * A[(int64_t)k * ld + c];
+    }
+    __syncthreads();
+    for (int r = tid; r < n; r += nt)
+      if (r != k) A[(int64_t)r * ld + k] = 0.0;
+    __syncthreads();
+  }
+  for (int64_t e = tid; e < (int64_t)n * n; e += nt) {
+    const int r = (int)(e / n), c = (int)(e % n);
+    inv[(int64_t)c * n + r] = A[(int64_t)r * ld + n + c];
+  }
+}
+
+__global__ void k_coarse_apply(int n, const double* __restrict__ inv, const double* __restrict__ b,
+                               double* __restrict__ x) {
+  extern __shared__ double s_b[];
+  for (int c = threadIdx.x; c < n; c += blockDim.x) s_b[c] = b[c];
+  __syncthreads();
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int c = 0; c < n; ++c) s += inv[(int64_t)c * n + r] * s_b[c];
+    x[r] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GMRES kernels
+// partial sums of V_k . w for k = k0 .. k0+nv-1 (nv <= GM_CHUNK); partials[(k0 + k) * nparts + block]
+__global__ void __launch_bounds__(256)
+k_multi_dot(int64_t Vown, const double2* __restrict__ Vb, int64_t stride2, int k0, int nv,
+            const double2* __restrict__ w, int nparts, double* __restrict__ partials) {
+  __shared__ double s_red[32];
+  double acc[GM_CHUNK];
+#pragma unroll
+  for (int k = 0; k < GM_CHUNK; ++k) acc[k] = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vown; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 wi = w[i];
+#pragma unroll
+    for (int k = 0; k < GM_CHUNK; ++k)
+      if (k < nv) {
+        const double2 v = Vb[(int64_t)(k0 + k) * stride2 + i];
+        acc[k] += v.x * wi.x + v.y * wi.y;
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < GM_CHUNK; ++k)
+    if (k < nv) {
+      const double r = lvpp_block_sum<256>(acc[k], s_red);
+      if (threadIdx.x == 0) partials[(int64_t)(k0 + k) * nparts + blockIdx.x] = r;
+    }
+}
+
+// w -= sum_k hc[k] V_k (k < nv); partial ||w_new||^2 into partials[slot * nparts + block]
+__global__ void __launch_bounds__(256)
+k_gmres_update(int64_t Vown, const double2* __restrict__ Vb, int64_t stride2, int nv, const double* __restrict__ hc,
+               double2* __restrict__ w, int nparts, int slot, double* __restrict__ partials) {
+  __shared__ double s_red[32];
+  double part = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vown; i += (int64_t)gridDim.x * blockDim.x) {
+    double2 wi = w[i];
+    for (int k = 0; k < nv; ++k) {
+      const double2 v = Vb[(int64_t)k * stride2 + i];
+      const double c = hc[k];
+      wi.x -= c * v.x;
+      wi.y -= c * v.y;
+    }
+    w[i] = wi;
+    part += wi.x * wi.x + wi.y * wi.y;
+  }
+  const double r = lvpp_block_sum<256>(part, s_red);
+  if (threadIdx.x == 0) partials[(int64_t)slot * nparts + blockIdx.x] = r;
+}
+
+// out = sum_k yc[k] V_k
+__global__ void __launch_bounds__(256)
+k_lincomb(int64_t Vown, const double2* __restrict__ Vb, int64_t stride2, int nv, const double* __restrict__ yc,
+          double2* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vown; i += (int64_t)gridDim.x * blockDim.x) {
+    double2 s = make_double2(0.0, 0.0);
+    for (int k = 0; k < nv; ++k) {
+      const double2 v = Vb[(int64_t)k * stride2 + i];
+      const double c = yc[k];
+      s.x += c * v.x;
+      s.y += c * v.y;
+    }
+    out[i] = s;
+  }
+}
+// y = a * x (+ y if accumulate)
+__global__ void k_axpby(int64_t Vown, double a, const double2* __restrict__ x, int accumulate, double2* __restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vown; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 v = x[i];
+    double2 o = accumulate ? y[i] : make_double2(0.0, 0.0);
+    o.x += a * v.x;
+    o.y += a * v.y;
+    y[i] = o;
+  }
+}
+__global__ void __launch_bounds__(256) k_reduce_multi(int nparts, int nvals, const double* __restrict__ partials,
+                                                       double* __restrict__ out) {
+  __shared__ double s_red[32];
+  for (int v = blockIdx.x; v < nvals; v += gridDim.x) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += 256) s += partials[(int64_t)v * nparts + i];
+    const double r = lvpp_block_sum<256>(s, s_red);
+    if (threadIdx.x == 0) out[v] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// hierarchy construction
+static int level_alloc_vectors(lvpp_problem* h, MgLevel& L) {
+  CKR(lvpp_dalloc(h, &L.binv, (size_t)4 * L.Vown));
+  CKR(lvpp_dalloc(h, &L.b, (size_t)2 * L.V));
+  CKR(lvpp_dalloc(h, &L.x, (size_t)2 * L.V));
+  CKR(lvpp_dalloc(h, &L.t, (size_t)2 * L.V));
+  return 0;
+}
+
+// builds level l + 1 from level l (single rank or replicated levels: no ghosts)
+static int build_next_level(lvpp_problem* h, int l, bool* stop) {
+  MgLevel& F = h->levels[l];
+  *stop = false;
+  const int64_t n = F.Vown;
+  // ---- aggregation: sort owned nodes by (Dirichlet bit, box / 2)
+  uint64_t *keys = nullptr, *skeys = nullptr;
+  uint32_t *vals = nullptr, *svals = nullptr;
+  int64_t* scan = nullptr;
+  CKR(lvpp_dalloc(h, &keys, (size_t)n, false));
+  CKR(lvpp_dalloc(h, &skeys, (size_t)n, false));
+  CKR(lvpp_dalloc(h, &vals, (size_t)n, false));
+  CKR(lvpp_dalloc(h, &svals, (size_t)n, false));
+  CKR(lvpp_dalloc(h, &scan, (size_t)n, false));
+  LAUNCH(h, k_agg_keys, lvpp_grid(n, 256, 16), 256, 0, n, F.box, F.bc_flag, keys, vals);
+  CK(cudaGetLastError());
+  size_t tb = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, skeys, vals, svals, n, 0, 63, h->stream));
+  void* tmp = nullptr;
+  CKR(lvpp_dalloc(h, (char**)&tmp, tb, false));
+  CK(cub::DeviceRadixSort::SortPairs(tmp, tb, keys, skeys, vals, svals, n, 0, 63, h->stream));
+  LAUNCH(h, k_heads, lvpp_grid(n, 256, 16), 256, 0, n, skeys, scan);
+  CK(cudaGetLastError());
+  size_t sb = 0;
+  CK(cub::DeviceScan::InclusiveSum(nullptr, sb, scan, scan, n, h->stream));
+  void* stmp = nullptr;
+  CKR(lvpp_dalloc(h, (char**)&stmp, sb, false));
+  CK(cub::DeviceScan::InclusiveSum(stmp, sb, scan, scan, n, h->stream));
+  int64_t Vc = 0;
+  CK(cudaMemcpyAsync(&Vc, scan + (n - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (Vc >= n || (double)Vc > 0.75 * (double)n) {  // no useful coarsening
+    *stop = true;
+    for (void* p : {(void*)keys, (void*)skeys, (void*)vals, (void*)svals, (void*)scan, tmp, stmp}) CKR(lvpp_dfree(h, p));
+    return 0;
+  }
+  MgLevel C;
+  C.V = C.Vown = Vc;
+  CKR(lvpp_dalloc(h, &F.agg, (size_t)F.V));
+  CKR(lvpp_dalloc(h, &F.agg_members, (size_t)n, false));
+  CKR(lvpp_dalloc(h, &F.agg_ptr, (size_t)Vc + 1));
+  CKR(lvpp_dalloc(h, &C.box, (size_t)3 * Vc));
+  CKR(lvpp_dalloc(h, &C.bc_flag, (size_t)Vc));
+  LAUNCH(h, k_agg_fill, lvpp_grid(n, 256, 16), 256, 0, n, skeys, svals, scan, F.agg, F.agg_members, F.agg_ptr,
+         C.box, C.bc_flag);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  for (void* p : {(void*)keys, (void*)skeys, (void*)vals, (void*)svals, (void*)scan, tmp, stmp}) CKR(lvpp_dfree(h, p));
+
+  // ---- coarse pattern and the Galerkin slot map: sort every fine slot by (coarse row, coarse col)
+  const int64_t S = F.slots;
+  if (S >= (int64_t)0xffffffffLL) { lvpp_set_error("too many slots for the 32-bit Galerkin map"); return LVPP_E_CAPACITY; }
+  CKR(lvpp_dalloc(h, &keys, (size_t)S, false));
+  CKR(lvpp_dalloc(h, &skeys, (size_t)S, false));
+  CKR(lvpp_dalloc(h, &vals, (size_t)S, false));
+  CKR(lvpp_dalloc(h, &F.gal_src, (size_t)S, false));
+  CK(cudaMemsetAsync(keys, 0xff, sizeof(uint64_t) * S, h->stream));  // slots of non-existent rows sort last
+  LAUNCH(h, k_gal_keys, lvpp_grid(n, 256, 16), 256, 0, n, F.slice_ptr, F.col, F.agg, keys, vals);
+  CK(cudaGetLastError());
+  tb = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, skeys, vals, F.gal_src, S, 0, 64, h->stream));
+  CKR(lvpp_dalloc(h, (char**)&tmp, tb, false));
+  CK(cub::DeviceRadixSort::SortPairs(tmp, tb, keys, skeys, vals, F.gal_src, S, 0, 64, h->stream));
+  // number of valid slots = slots of existing rows
+  int64_t sp_last[2];
+  CK(cudaMemcpyAsync(sp_last, F.slice_ptr + (F.nslices - 1), 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const int64_t w_last = (sp_last[1] - sp_last[0]) / LVPP_SLICE;
+  const int64_t nvalid = S - (F.nslices * LVPP_SLICE - n) * w_last;
+  int64_t* scan2 = (int64_t*)keys;  // keys are no longer needed after the sort
+  LAUNCH(h, k_heads, lvpp_grid(nvalid, 256, 16), 256, 0, nvalid, skeys, scan2);
+  CK(cudaGetLastError());
+  sb = 0;
+  CK(cub::DeviceScan::InclusiveSum(nullptr, sb, scan2, scan2, nvalid, h->stream));
+  CKR(lvpp_dalloc(h, (char**)&stmp, sb, false));
+  CK(cub::DeviceScan::InclusiveSum(stmp, sb, scan2, scan2, nvalid, h->stream));
+  int64_t nnzc = 0;
+  CK(cudaMemcpyAsync(&nnzc, scan2 + (nvalid - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  C.nnz = nnzc;
+  uint64_t* ukeys = nullptr;
+  CKR(lvpp_dalloc(h, &ukeys, (size_t)nnzc, false));
+  CKR(lvpp_dalloc(h, &F.gal_ptr, (size_t)nnzc + 1, false));
+  CKR(lvpp_dalloc(h, &F.gal_dst, (size_t)nnzc, false));
+  LAUNCH(h, k_compact_heads, lvpp_grid(nvalid, 256, 16), 256, 0, nvalid, skeys, scan2, ukeys, F.gal_ptr, nvalid);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(F.gal_ptr + nnzc, &nvalid, sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+  // coarse rows
+  int64_t* rowstart = nullptr;
+  int* d_err = nullptr;
+  CKR(lvpp_dalloc(h, &rowstart, (size_t)Vc + 1));
+  CKR(lvpp_dalloc(h, &d_err, 1));
+  CKR(lvpp_dalloc(h, &C.rowlen, (size_t)Vc));
+  LAUNCH(h, k_coarse_rowstart, lvpp_grid(Vc + 1, 256, 16), 256, 0, Vc, nnzc, ukeys, rowstart, C.rowlen);
+  LAUNCH(h, k_coarse_rowlen, lvpp_grid(Vc, 256, 16), 256, 0, Vc, rowstart, C.rowlen, d_err);
+  CK(cudaGetLastError());
+  C.nslices = (Vc + LVPP_SLICE - 1) / LVPP_SLICE;
+  int64_t* slots = nullptr;
+  CKR(lvpp_dalloc(h, &slots, (size_t)C.nslices + 1));
+  CKR(lvpp_dalloc(h, &C.slice_ptr, (size_t)C.nslices + 1));
+  LAUNCH(h, k_slice_slots, lvpp_grid((C.nslices + 1) * 32, 256, 16), 256, 0, C.nslices, Vc, C.rowlen, slots);
+  CK(cudaGetLastError());
+  size_t sb2 = 0;
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, sb2, slots, C.slice_ptr, C.nslices + 1, h->stream));
+  void* stmp2 = nullptr;
+  CKR(lvpp_dalloc(h, (char**)&stmp2, sb2, false));
+  CK(cub::DeviceScan::ExclusiveSum(stmp2, sb2, slots, C.slice_ptr, C.nslices + 1, h->stream));
+  int herr = 0;
+  CK(cudaMemcpyAsync(&C.slots, C.slice_ptr + C.nslices, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (herr) { lvpp_set_error("a coarse row has more than %d entries", LVPP_MAX_ROW); return LVPP_E_CAPACITY; }
+  CKR(lvpp_dalloc(h, &C.col, (size_t)C.slots));
+  CKR(lvpp_dalloc(h, &C.diag_k, (size_t)Vc));
+  CKR(lvpp_dalloc(h, &C.K, (size_t)C.slots));
+  CKR(lvpp_dalloc(h, &C.M, (size_t)C.slots));
+  CKR(lvpp_dalloc(h, &C.D, (size_t)C.slots));
+  LAUNCH(h, k_coarse_cols, lvpp_grid(Vc, 256, 16), 256, 0, Vc, rowstart, ukeys, C.slice_ptr, C.bc_flag, C.col,
+         C.diag_k, F.gal_dst);
+  CK(cudaGetLastError());
+  // constant operators of the coarse level
+  LAUNCH(h, k_galerkin, lvpp_grid(nnzc, 256, 16), 256, 0, nnzc, F.gal_ptr, F.gal_src, F.gal_dst, 2, F.K, F.M, C.K, C.M);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  for (void* p : {(void*)keys, (void*)skeys, (void*)vals, tmp, stmp, (void*)ukeys, (void*)rowstart, (void*)d_err,
+                  (void*)slots, stmp2})
+    CKR(lvpp_dfree(h, p));
+  CKR(level_alloc_vectors(h, C));
+  h->levels.push_back(C);
+  return 0;
+}
+
+int lvpp_mg_setup(lvpp_problem* h) {
+  if (h->mg_ready) return 0;
+  if (h->nranks > 1) { lvpp_set_error("multigrid preconditioner: multi-GPU hierarchy not built"); return LVPP_E_INVALID; }
+  h->levels.clear();
+  MgLevel L0;
+  L0.V = h->V; L0.Vown = h->Vown; L0.nslices = h->nslices; L0.slots = h->sell_slots; L0.nnz = h->scalar_nnz;
+  L0.slice_ptr = h->slice_ptr; L0.col = h->col; L0.rowlen = h->rowlen; L0.diag_k = h->diag_k;
+  L0.K = h->K; L0.M = h->M; L0.D = h->D; L0.bc_flag = h->bc_flag;
+  CKR(lvpp_dalloc(h, &L0.box, (size_t)3 * L0.Vown));
+  LAUNCH(h, k_box0, lvpp_grid(L0.Vown, 256, 16), 256, 0, L0.Vown, h->tdim, h->coords, h->xmin[0], h->xmin[1],
+         h->xmin[2], 1.0 / h->h0, L0.box);
+  CK(cudaGetLastError());
+  CKR(level_alloc_vectors(h, L0));
+  h->levels.push_back(L0);
+  for (int l = 0; l < MG_MAX_LEVELS - 1; ++l) {
+    if (h->levels[l].Vown <= MG_COARSE_TARGET) break;
+    bool stop = false;
+    CKR(build_next_level(h, l, &stop));
+    if (stop) break;
+  }
+  const MgLevel& Lc = h->levels.back();
+  if (Lc.Vown > MG_COARSE_MAX) {
+    lvpp_set_error("multigrid: coarsening stalled at %lld nodes (limit %d)", (long long)Lc.Vown, MG_COARSE_MAX);
+    return LVPP_E_CAPACITY;
+  }
+  h->coarse_n = (int)(2 * Lc.Vown);
+  CKR(lvpp_dalloc(h, &h->coarse_lu, (size_t)h->coarse_n * h->coarse_n));
+  // GMRES workspace
+  h->gm_restart = 40;
+  CKR(lvpp_dalloc(h, &h->gm_V, (size_t)(h->gm_restart + 1) * 2 * h->V));
+  CKR(lvpp_dalloc(h, &h->gm_h, (size_t)h->gm_restart + 8));
+  CK(cudaMallocHost((void**)&h->gm_h_host, sizeof(double) * (h->gm_restart + 8)));
+  CK(cudaStreamSynchronize(h->stream));
+  h->mg_ready = true;
+  return 0;
+}
+
+// per Newton step: coarse D, node-block inverses, dense inverse of the coarsest operator
+int lvpp_mg_update(lvpp_problem* h) {
+  CKR(lvpp_mg_setup(h));
+  const int nl = (int)h->levels.size();
+  for (int l = 0; l + 1 < nl; ++l) {
+    MgLevel& F = h->levels[l];
+    MgLevel& C = h->levels[l + 1];
+    LAUNCH(h, k_galerkin, lvpp_grid(C.nnz, 256, 16), 256, 0, C.nnz, F.gal_ptr, F.gal_src, F.gal_dst, 1, F.D, F.D, C.D, C.D);
+    CK(cudaGetLastError());
+  }
+  for (int l = 0; l < nl; ++l) {
+    MgLevel& L = h->levels[l];
+    LAUNCH(h, k_build_binv, lvpp_grid(L.Vown, 256, 8), 256, 0, L.Vown, L.slice_ptr, L.diag_k, L.K, L.M, L.D,
+           L.bc_flag, h->alpha, h->mg_omega, L.binv);
+    CK(cudaGetLastError());
+  }
+  MgLevel& Lc = h->levels.back();
+  const int n = h->coarse_n;
+  double* aug = nullptr;
+  int* d_err = nullptr;
+  CKR(lvpp_dalloc(h, &aug, (size_t)n * 2 * n));
+  CKR(lvpp_dalloc(h, &d_err, 1));
+  LAUNCH(h, k_coarse_dense, lvpp_grid(Lc.Vown, 128, 4), 128, 0, Lc.Vown, Lc.slice_ptr, Lc.rowlen, Lc.col, Lc.K, Lc.M,
+         Lc.D, Lc.bc_flag, h->alpha, aug);
+  LAUNCH(h, k_gauss_jordan, 1, 1024, 0, n, aug, h->coarse_lu, d_err);
+  CK(cudaGetLastError());
+  int herr = 0;
+  CK(cudaMemcpyAsync(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CKR(lvpp_dfree(h, aug));
+  CKR(lvpp_dfree(h, d_err));
+  if (herr) { lvpp_set_error("multigrid: singular coarsest operator"); return LVPP_E_INVALID; }
+  return 0;
+}
+
+static int level_op(lvpp_problem* h, MgLevel& L, int epi, const double* v, const double* b, double* y) {
+  OpArgs p = lvpp_level_op(h, L);
+  p.v = (const double2*)v;
+  p.y = (double2*)y;
+  p.epi = epi;
+  p.b = (const double2*)b;
+  p.binv = L.binv;
+  p.omega = h->mg_omega;
+  const int grid = lvpp_grid(L.Vown, 256, 6);
+  LAUNCH(h, k_block_op<0>, grid, 256, 0, p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// z = V-cycle(b) with zero initial guess on level 0; returns the buffer that holds z
+int lvpp_mg_vcycle(lvpp_problem* h, const double* b_in, double** z_out) {
+  const int nl = (int)h->levels.size();
+  std::vector<double*> cur(nl), oth(nl);
+  std::vector<const double*> rhs(nl);
+  const int nsm = h->mg_nsmooth;
+  rhs[0] = b_in;
+  for (int l = 0; l < nl - 1; ++l) {
+    MgLevel& L = h->levels[l];
+    cur[l] = L.x; oth[l] = L.t;
+    LAUNCH(h, k_smooth_first, lvpp_grid(L.Vown, 256, 6), 256, 0, L.Vown, (const double2*)rhs[l], L.binv, h->mg_omega,
+           (double2*)cur[l]);
+    CK(cudaGetLastError());
+    for (int s = 1; s < nsm; ++s) {
+      CKR(level_op(h, L, EPI_JACOBI, cur[l], rhs[l], oth[l]));
+      std::swap(cur[l], oth[l]);
+    }
+    CKR(level_op(h, L, EPI_RESID, cur[l], rhs[l], oth[l]));  // residual into the spare buffer
+    MgLevel& C = h->levels[l + 1];
+    LAUNCH(h, k_restrict, lvpp_grid(C.Vown, 256, 6), 256, 0, C.Vown, L.agg_ptr, L.agg_members, (const double2*)oth[l],
+           C.bc_flag, (double2*)C.b);
+    CK(cudaGetLastError());
+    rhs[l + 1] = C.b;
+  }
+  {  // coarsest: x = inv * b
+    MgLevel& L = h->levels[nl - 1];
+    cur[nl - 1] = L.x; oth[nl - 1] = L.t;
+    const int n = h->coarse_n;
+    LAUNCH(h, k_coarse_apply, (n + 127) / 128, 128, sizeof(double) * n, n, h->coarse_lu, rhs[nl - 1], cur[nl - 1]);
+    CK(cudaGetLastError());
+  }
+  for (int l = nl - 2; l >= 0; --l) {
+    MgLevel& L = h->levels[l];
+    LAUNCH(h, k_prolong_add, lvpp_grid(L.Vown, 256, 6), 256, 0, L.Vown, L.agg, (const double2*)cur[l + 1], L.bc_flag,
+           h->mg_over, (double2*)cur[l]);
+    CK(cudaGetLastError());
+    for (int s = 0; s < nsm; ++s) {
+      CKR(level_op(h, L, EPI_JACOBI, cur[l], rhs[l], oth[l]));
+      std::swap(cur[l], oth[l]);
+    }
+  }
+  h->vcycles++;
+  *z_out = cur[0];
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// right-preconditioned restarted GMRES:  J M^-1 (M y) = rhs
+static int reduce_to_host(lvpp_problem* h, double* partials, int nvals, double* dst_dev, double* dst_host) {
+  LAUNCH(h, k_reduce_multi, nvals < 64 ? nvals : 64, 256, 0, h->npartials, nvals, partials, dst_dev);
+  CK(cudaGetLastError());
+  if (h->nranks > 1) CKR(lvpp_allreduce_sum(h, dst_dev, nvals));
+  CK(cudaMemcpyAsync(dst_host, dst_dev, sizeof(double) * nvals, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_newton_opts* o, int32_t* its_out,
+                  int32_t* reason_out, double* rnorm_out) {
+  const int m = h->gm_restart;
+  const int64_t Vown = h->Vown, stride2 = h->V;  // basis vectors are 2V doubles = V double2
+  const int nb = h->npartials;
+  double2* Vb = (double2*)h->gm_V;
+  double* gpart = nullptr;  // partial sums [(m + 2) * nb]
+  CKR(lvpp_dalloc(h, &gpart, (size_t)(m + 2) * nb));
+  const int maxit = o->ksp_max_it > 0 ? o->ksp_max_it : 1000;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), yv(m);
+  auto vec = [&](int k) { return (double*)(Vb + (int64_t)k * stride2); };
+  int total = 0, reason = 0;
+  double bnorm = 0.0, rnorm = 0.0, tol = 0.0;
+  bool first = true;
+  MgLevel& L0 = h->levels[0];
+  CK(cudaMemsetAsync(d_y, 0, sizeof(double) * 2 * h->V, h->stream));
+  while (reason == 0) {
+    // r = rhs - J y  (first cycle: y = 0)
+    if (first) {
+      CK(cudaMemcpyAsync(vec(0), d_rhs, sizeof(double) * 2 * Vown, cudaMemcpyDeviceToDevice, h->stream));
+    } else {
+      if (h->nranks > 1) CKR(lvpp_halo_forward_impl(h, d_y));
+      CKR(level_op(h, L0, EPI_RESID, d_y, d_rhs, vec(0)));
+    }
+    LAUNCH(h, k_multi_dot, nb, 256, 0, Vown, Vb, stride2, 0, 1, (const double2*)vec(0), nb, gpart);
+    CK(cudaGetLastError());
+    CKR(reduce_to_host(h, gpart, 1, h->gm_h, h->gm_h_host));
+    rnorm = sqrt(h->gm_h_host[0]);
+    if (first) {
+      bnorm = rnorm;
+      tol = std::max(o->ksp_rtol * bnorm, o->ksp_atol);
+      first = false;
+    }
+    if (!std::isfinite(rnorm)) { reason = LVPP_KSP_DIVERGED_NANORINF; break; }
+    if (rnorm <= tol) { reason = rnorm <= o->ksp_atol ? LVPP_KSP_CONVERGED_ATOL : LVPP_KSP_CONVERGED_RTOL; break; }
+    LAUNCH(h, k_axpby, nb, 256, 0, Vown, 1.0 / rnorm, (const double2*)vec(0), 0, (double2*)vec(0));
+    CK(cudaGetLastError());
+    std::fill(g.begin(), g.end(), 0.0);
+    g[0] = rnorm;
+    int j = 0;
+    for (; j < m; ++j) {
+      // w = J M^-1 v_j  -> stored in v_{j+1}
+      double* z = nullptr;
+      CKR(lvpp_mg_vcycle(h, vec(j), &z));
+      if (h->nranks > 1) CKR(lvpp_halo_forward_impl(h, z));
+      CK(cudaEventRecord(h->evs0, h->stream));
+      CKR(level_op(h, L0, EPI_NONE, z, nullptr, vec(j + 1)));
+      CK(cudaEventRecord(h->evs1, h->stream));
+      double* hcol = &H[(size_t)j * (m + 1)];
+      for (int k = 0; k <= j + 1; ++k) hcol[k] = 0.0;
+      double beta = 0.0;
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int k0 = 0; k0 <= j; k0 += GM_CHUNK) {
+          const int nv = std::min(GM_CHUNK, j + 1 - k0);
+          LAUNCH(h, k_multi_dot, nb, 256, 0, Vown, Vb, stride2, k0, nv, (const double2*)vec(j + 1), nb, gpart);
+        }
+        CK(cudaGetLastError());
+        CKR(reduce_to_host(h, gpart, j + 1, h->gm_h, h->gm_h_host));
+        double hsq = 0.0;
+        for (int k = 0; k <= j; ++k) { hcol[k] += h->gm_h_host[k]; hsq += h->gm_h_host[k] * h->gm_h_host[k]; }
+        // coefficients are already on the device in gm_h (all-reduced)
+        LAUNCH(h, k_gmres_update, nb, 256, 0, Vown, Vb, stride2, j + 1, h->gm_h, (double2*)vec(j + 1), nb, m + 1, gpart);
+        CK(cudaGetLastError());
+        CKR(reduce_to_host(h, gpart + (size_t)(m + 1) * nb, 1, h->gm_h + m + 2, h->gm_h_host + m + 2));
+        beta = sqrt(h->gm_h_host[m + 2]);
+        if (pass == 0) {
+          float sms = 0.f;
+          CK(cudaEventElapsedTime(&sms, h->evs0, h->evs1));
+          h->spmv_sampled_ms += sms;
+          h->spmv_samples++;
+        }
+        // selective re-orthogonalisation (Daniel et al.): only when the projection removed most of w
+        if (beta * beta > 0.5 * (hsq + beta * beta)) break;
+      }
+      hcol[j + 1] = beta;
+      ++total;
+      // Givens
+      for (int k = 0; k < j; ++k) {
+        const double t = cs[k] * hcol[k] + sn[k] * hcol[k + 1];
+        hcol[k + 1] = -sn[k] * hcol[k] + cs[k] * hcol[k + 1];
+        hcol[k] = t;
+      }
+      const double den = std::hypot(hcol[j], hcol[j + 1]);
+      cs[j] = den > 0 ? hcol[j] / den : 1.0;
+      sn[j] = den > 0 ? hcol[j + 1] / den : 0.0;
+      hcol[j] = den;
+      hcol[j + 1] = 0.0;
+      g[j + 1] = -sn[j] * g[j];
+      g[j] = cs[j] * g[j];
+      rnorm = fabs(g[j + 1]);
+      if (!std::isfinite(rnorm)) { reason = LVPP_KSP_DIVERGED_NANORINF; ++j; break; }
+      const bool conv = rnorm <= tol;
+      if (conv || beta == 0.0 || total >= maxit) {
+        ++j;
+        if (conv) reason = rnorm <= o->ksp_atol ? LVPP_KSP_CONVERGED_ATOL : LVPP_KSP_CONVERGED_RTOL;
+        else if (beta == 0.0) reason = LVPP_KSP_CONVERGED_RTOL;  // happy breakdown: exact solution in the space
+        else reason = LVPP_KSP_DIVERGED_ITS;
+        break;
+      }
+      LAUNCH(h, k_axpby, nb, 256, 0, Vown, 1.0 / beta, (const double2*)vec(j + 1), 0, (double2*)vec(j + 1));
+      CK(cudaGetLastError());
+    }
+    const int k = j;  // columns used
+    if (reason == LVPP_KSP_DIVERGED_NANORINF) break;
+    // back substitution, y += M^-1 (V yv)
+    for (int i = k - 1; i >= 0; --i) {
+      double s = g[i];
+      for (int c = i + 1; c < k; ++c) s -= H[(size_t)c * (m + 1) + i] * yv[c];
+      yv[i] = s / H[(size_t)i * (m + 1) + i];
+    }
+    for (int i = 0; i < k; ++i) h->gm_h_host[i] = yv[i];
+    CK(cudaMemcpyAsync(h->gm_h, h->gm_h_host, sizeof(double) * k, cudaMemcpyHostToDevice, h->stream));
+    // the combination goes to v_m (free: k <= m columns use v_0..v_{k-1}; v_k holds w and is dead)
+    double* comb = vec(k);
+    LAUNCH(h, k_lincomb, nb, 256, 0, Vown, Vb, stride2, k, h->gm_h, (double2*)comb);
+    CK(cudaGetLastError());
+    double* z = nullptr;
+    CKR(lvpp_mg_vcycle(h, comb, &z));
+    LAUNCH(h, k_axpby, nb, 256, 0, Vown, 1.0, (const double2*)z, 1, (double2*)d_y);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));  // gm_h_host is reused by the next cycle
+  }
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaEventSynchronize(h->ev1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->t_krylov_ms += ms;
+  h->krylov_its += total;
+  CKR(lvpp_dfree(h, gpart));
+  if (its_out) *its_out = total;
+  if (reason_out) *reason_out = reason;
+  if (rnorm_out) *rnorm_out = rnorm;
+  return 0;
+}

@@ -390,6 +390,36 @@ extern "C" int lvpp_create(const lvpp_obstacle_desc* d, lvpp_handle* out) {
       CKR(lvpp_dalloc(h, &h->recv_buf, (size_t)2 * nr));
     }
     CK(cudaStreamSynchronize(h->stream));
+    {  // node spacing and origin for the coordinate aggregation of the multigrid hierarchy
+      const int td = h->tdim, nv = td + 1;
+      for (int dd = 0; dd < 3; ++dd) h->xmin[dd] = 0.0;
+      for (int dd = 0; dd < td; ++dd) {
+        double mn = d->node_coords[dd];
+        for (int64_t i = 1; i < h->Vown; ++i) mn = std::min(mn, d->node_coords[i * td + dd]);
+        h->xmin[dd] = mn;
+      }
+      const int64_t nsample = std::min<int64_t>(h->C, 200000);
+      const int64_t step = std::max<int64_t>(1, h->C / nsample);
+      std::vector<double> mins;
+      mins.reserve((size_t)nsample + 1);
+      for (int64_t c = 0; c < h->C; c += step) {
+        double best = 1e300;
+        for (int a = 0; a < nv; ++a)
+          for (int b = a + 1; b < nv; ++b) {
+            double s2 = 0.0;
+            for (int dd = 0; dd < td; ++dd) {
+              const double t = d->node_coords[(int64_t)d->cell_nodes[c * h->nld + a] * td + dd] -
+                               d->node_coords[(int64_t)d->cell_nodes[c * h->nld + b] * td + dd];
+              s2 += t * t;
+            }
+            best = std::min(best, s2);
+          }
+        mins.push_back(std::sqrt(best));
+      }
+      std::nth_element(mins.begin(), mins.begin() + mins.size() / 2, mins.end());
+      h->h0 = mins[mins.size() / 2] / (h->nld > nv ? 2.0 : 1.0);  // P2: edge midpoints halve the spacing
+      if (!(h->h0 > 0.0)) { lvpp_set_error("degenerate mesh (zero edge length)"); return LVPP_E_INVALID; }
+    }
     CKR(lvpp_build_pattern(h));
     // operator storage
     CKR(lvpp_dalloc(h, &h->K, (size_t)h->sell_slots));
@@ -429,6 +459,7 @@ extern "C" int lvpp_destroy(lvpp_handle h) {
   if (h->flush) cudaFree(h->flush);
   if (h->scal_host) cudaFreeHost(h->scal_host);
   if (h->red_host) cudaFreeHost(h->red_host);
+  if (h->gm_h_host) cudaFreeHost(h->gm_h_host);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->evs0) cudaEventDestroy(h->evs0);

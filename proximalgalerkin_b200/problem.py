@@ -349,13 +349,21 @@ def newton_options(options):
     if st != "newtonls":
         raise NotImplementedError(f"snes_type {st!r}")
     kt = opts.get("ksp_type", "preonly")
-    if kt not in ("preonly", "minres"):
-        raise NotImplementedError(f"ksp_type {kt!r}: the Newton system is solved with block-preconditioned MINRES")
+    if kt not in ("preonly", "minres", "gmres", "fgmres"):
+        raise NotImplementedError(f"ksp_type {kt!r}: the Newton system is solved with MINRES or GMRES")
     pc = opts.get("pc_type", "lu")
-    if pc in ("lu", "jacobi", "fieldsplit", "none"):
+    if pc in ("mg", "gamg") or (pc == "lu" and kt in ("gmres", "fgmres")):
+        # monolithic aggregation multigrid + restarted GMRES
+        o.pc_type = _capi.PC_MG
+        o.ksp_max_it = 2000
+    elif pc in ("lu", "jacobi", "fieldsplit", "none"):
+        if kt in ("gmres", "fgmres"):
+            raise NotImplementedError("GMRES is paired with pc_type mg")
         o.pc_type = _capi.PC_JACOBI
     else:
         raise NotImplementedError(f"pc_type {pc!r}")
+    if opts.get("pc_mg_smoothing_sweeps") is not None:
+        o.pc_degree = int(opts["pc_mg_smoothing_sweeps"])
     for key, field, cast in (
         ("snes_rtol", "snes_rtol", float),
         ("snes_atol", "snes_atol", float),
