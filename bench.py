@@ -173,6 +173,8 @@ def run_b200(args):
     msh = lvpp.mesh.create_box(n, n, n * world, lo=(-1.0, -1.0, -float(world)), hi=(1.0, 1.0, float(world)),
                                rank=rank, nranks=world)
     opts = {"ksp_rtol": args.ksp_rtol, "ksp_max_it": 200000}
+    if args.pc == "mg":
+        opts = {"ksp_rtol": args.ksp_rtol, "ksp_type": "gmres", "pc_type": "mg"}
     st = lvpp.obstacle_pg.LvppStepper(msh, 1, "double_exponential", 1e2, 1e-4, petsc_options=opts)
     dev = st.dev
     stats0 = dev.stats()
@@ -302,7 +304,8 @@ def run_b200(args):
             "config": {"workload": f"3-D P1 obstacle LVPP (configs[1]): {n}x{n}x{n * world} cubes x 6 tets, "
                                    f"{rows_global} rows, {stats0['nnz']} nnz/GPU (CSR-equivalent)",
                        "n": n, "rows": rows_global, "alpha_scheme": "double_exponential", "alpha_max": 1e2,
-                       "snes_rtol": 1e-6, "ksp": "MINRES + block-Jacobi/Schur-diag", "ksp_rtol": args.ksp_rtol,
+                       "snes_rtol": 1e-6, "ksp": ("MINRES + block-Jacobi/Schur-diag" if args.pc == "jacobi" else
+                               "GMRES(40) + monolithic aggregation multigrid (node-block Jacobi smoother)"), "ksp_rtol": args.ksp_rtol,
                        "l2": "operator (>=4 GB) and vectors exceed the 126 MB L2; no flush needed" if n >= 100 else
                              "inputs fit L2: kernel-level numbers are L2-warm",
                        "parallelism": f"slab{world}"},
@@ -324,6 +327,8 @@ def main():
     ap.add_argument("--cpu-size", dest="n_cpu", type=int, default=16, help="cubes per axis of the CPU sample")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ksp-rtol", dest="ksp_rtol", type=float, default=1e-12)
+    ap.add_argument("--pc", default="jacobi", choices=["jacobi", "mg"],
+                    help="jacobi: block-diagonal MINRES; mg: multigrid-preconditioned GMRES")
     ap.add_argument("--skip-e2e", dest="no_e2e", action="store_true")
     ap.add_argument("--skip-cpu", dest="no_cpu", action="store_true")
     ap.add_argument("--skip-aux", dest="no_aux", action="store_true")

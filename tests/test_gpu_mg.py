@@ -1,0 +1,66 @@
+"""The multigrid-preconditioned GMRES path (pc_type mg) against the oracle: linear solves against
+sparse LU, and full LVPP solves with identical Newton / proximal iteration counts."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+pytestmark = pytest.mark.gpu
+MG = {"ksp_type": "gmres", "pc_type": "mg"}
+
+
+def _pair(kind, n, degree=1):
+    import proximalgalerkin_b200 as lvpp
+    from oracle import mesh as omesh
+    from oracle import obstacle as oobs
+
+    if kind == "tri":
+        msh, om = lvpp.mesh.create_rectangle(n, n), omesh.rectangle(n, n)
+    else:
+        msh, om = lvpp.mesh.create_box(n, n, n), omesh.box_kuhn(n, n, n)
+    s = lvpp.obstacle_pg.setup(msh, degree, obstacle="phi_set", petsc_options=MG)
+    return lvpp, s, s["problem"].device_problem, oobs.ObstacleOracle(om, degree=degree)
+
+
+@pytest.mark.parametrize("kind,n,degree", [("tri", 3, 1), ("tri", 40, 1), ("tet", 12, 1), ("tri", 12, 2), ("tet", 4, 2)])
+def test_mg_gmres_linear_solve(lib, kind, n, degree):
+    lvpp, s, dev, orc = _pair(kind, n, degree)
+    rng = np.random.default_rng(11)
+    x = 0.2 * rng.standard_normal(orc.num_rows)
+    x[1::2] -= 3.0 * (rng.random(orc.num_rows // 2) > 0.6)  # strongly varying exp(psi)
+    x[orc.bc_dofs] = 0.0
+    alpha = 7.5
+    dev.set_alpha(alpha)
+    dev.set_previous(np.zeros(orc.num_rows))
+    X, R, Y = (lvpp.DeviceVector(dev.n, dev.device) for _ in range(3))
+    X.set(x)
+    dev.assemble_jacobian(X)
+    J = orc.jacobian(x, alpha)
+    rhs = rng.standard_normal(orc.num_rows)
+    R.set(rhs)
+    opts = lvpp.newton_options(dict(MG, ksp_rtol=1e-12))
+    its, reason, rnorm = dev.linear_solve(R, Y, opts)
+    assert reason > 0, (its, reason, rnorm)
+    y = Y.numpy()
+    assert np.linalg.norm(J @ y - rhs) <= 5e-12 * np.linalg.norm(rhs)
+    ye = spla.splu(J.tocsc()).solve(rhs)
+    assert np.linalg.norm(y - ye) / np.linalg.norm(ye) < 1e-8
+    assert its < 80
+    Y2 = lvpp.DeviceVector(dev.n, dev.device)
+    its2, _, _ = dev.linear_solve(R, Y2, opts)
+    assert its2 == its and np.array_equal(y, Y2.numpy())  # bit-reproducible
+
+
+@pytest.mark.parametrize("kind,n,degree", [("tri", 20, 1), ("tet", 7, 1), ("tri", 8, 2)])
+def test_full_lvpp_solve_mg_matches_oracle(lib, kind, n, degree):
+    import proximalgalerkin_b200 as lvpp
+    from oracle import lvpp_driver
+
+    lvpp_, s, dev, orc = _pair(kind, n, degree)
+    xo, ho = lvpp_driver.solve_obstacle(orc, max_outer=500, alpha_scheme="double_exponential", alpha_max=1e2, tol_exit=1e-4)
+    sol, total, h = lvpp.obstacle_pg.solve_problem(s["V"].mesh, degree, 500, "double_exponential", 1e2, 1e-4, petsc_options=MG)
+    assert h["newton_steps"] == ho["newton_steps"]
+    assert h["reason"] == ho["reason"]
+    u, uo = sol.x.array[0::2], xo[0::2]
+    assert np.linalg.norm(u - uo) / np.linalg.norm(uo) < 1e-10
+    for key in ("energy", "complementarity", "feasibility", "dual_feasibility", "primal_increment", "latent_increment"):
+        assert np.allclose(h[key], ho[key], rtol=1e-7, atol=1e-12), key
