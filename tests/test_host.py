@@ -100,7 +100,11 @@ def test_option_parsing():
     assert o.ksp_rtol == 1e-12
     o = lvpp.newton_options({})
     assert (o.snes_rtol, o.snes_max_it) == (1e-8, 50)  # PETSc defaults
-    for bad in ({"snes_linesearch_type": "bt"}, {"ksp_type": "gmres"}, {"pc_type": "hypre"}, {"snes_type": "vinewtonssls"}):
+    assert lvpp.newton_options({"ksp_type": "gmres"}).pc_type == lvpp._capi.PC_MG
+    assert lvpp.newton_options({"ksp_type": "gmres", "pc_type": "mg", "pc_mg_smoothing_sweeps": 3}).pc_degree == 3
+    assert lvpp.newton_options({"ksp_type": "minres", "pc_type": "jacobi"}).pc_type == lvpp._capi.PC_JACOBI
+    for bad in ({"snes_linesearch_type": "bt"}, {"ksp_type": "gmres", "pc_type": "jacobi"}, {"ksp_type": "cg"},
+                {"pc_type": "hypre"}, {"snes_type": "vinewtonssls"}):
         with pytest.raises(NotImplementedError):
             lvpp.newton_options(bad)
 
