@@ -127,6 +127,11 @@ typedef struct lvpp_stats {
   double last_spmv_ms;       /* mean J*v kernel time of the last lvpp_time_spmv call */
   double spmv_sampled_ms;    /* cumulative CUDA-event time of the J*v launches sampled inside Krylov solves */
   int64_t spmv_samples;      /* number of sampled J*v launches (one per convergence poll) */
+  int64_t fine_op_launches;  /* cumulative launches of the block operator kernel on the fine level (J*v, residual
+                                and smoother sweeps of the multigrid cycle all run the same kernel) */
+  int64_t vcycles;           /* cumulative multigrid V-cycles */
+  int32_t mg_levels;         /* levels of the multigrid hierarchy (0 until first used) */
+  int32_t reserved0;
 } lvpp_stats;
 
 const char* lvpp_last_error(void);

@@ -99,6 +99,10 @@ class Stats(C.Structure):
         ("last_spmv_ms", C.c_double),
         ("spmv_sampled_ms", C.c_double),
         ("spmv_samples", C.c_int64),
+        ("fine_op_launches", C.c_int64),
+        ("vcycles", C.c_int64),
+        ("mg_levels", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
     def as_dict(self):

@@ -506,6 +506,7 @@ int lvpp_apply_jacobian(lvpp_problem* h, const double* d_v, double* d_y, const d
   p.y = (double2*)d_y;
   p.inv_scale = inv_scale;
   p.partials = partials;
+  h->fine_op_launches++;
   LAUNCH(h, k_block_op<0>, h->npartials, 256, 0, p);
   CK(cudaGetLastError());
   return 0;

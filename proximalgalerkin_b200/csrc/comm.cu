@@ -122,29 +122,46 @@ int lvpp_allreduce_sum(lvpp_problem* h, double* d_buf, int n) {
   return 0;
 }
 
-int lvpp_halo_forward_impl(lvpp_problem* h, double* d_v) {
-  if (h->nranks <= 1 || h->num_neighbors == 0) return 0;
+int lvpp_halo_forward_level(lvpp_problem* h, const LevelHalo& H, double* d_v) {
+  if (h->nranks <= 1 || H.num_neighbors == 0) return 0;
   if (!h->nccl_comm) { lvpp_set_error("communicator not initialised"); return LVPP_E_COMM; }
-  const int64_t ns = h->send_ptr.back(), nr = h->recv_ptr.back();
+  const int64_t ns = H.send_ptr.back(), nr = H.recv_ptr.back();
   if (ns > 0) {
-    LAUNCH(h, k_pack, lvpp_grid(ns, 256, 4), 256, 0, ns, h->send_nodes, (const double2*)d_v, (double2*)h->send_buf);
+    LAUNCH(h, k_pack, lvpp_grid(ns, 256, 4), 256, 0, ns, H.send_nodes, (const double2*)d_v, (double2*)H.send_buf);
     CK(cudaGetLastError());
   }
   NCK(g_nccl.GroupStart());
-  for (int b = 0; b < h->num_neighbors; ++b) {
-    const int64_t s0 = h->send_ptr[b], s1 = h->send_ptr[b + 1], r0 = h->recv_ptr[b], r1 = h->recv_ptr[b + 1];
+  for (int b = 0; b < H.num_neighbors; ++b) {
+    const int64_t s0 = H.send_ptr[b], s1 = H.send_ptr[b + 1], r0 = H.recv_ptr[b], r1 = H.recv_ptr[b + 1];
     if (s1 > s0)
-      NCK(g_nccl.Send(h->send_buf + 2 * s0, (size_t)(2 * (s1 - s0)), ncclDouble, h->neighbor_ranks[b],
+      NCK(g_nccl.Send(H.send_buf + 2 * s0, (size_t)(2 * (s1 - s0)), ncclDouble, H.neighbor_ranks[b],
                       (ncclComm_t)h->nccl_comm, h->stream));
     if (r1 > r0)
-      NCK(g_nccl.Recv(h->recv_buf + 2 * r0, (size_t)(2 * (r1 - r0)), ncclDouble, h->neighbor_ranks[b],
+      NCK(g_nccl.Recv(H.recv_buf + 2 * r0, (size_t)(2 * (r1 - r0)), ncclDouble, H.neighbor_ranks[b],
                       (ncclComm_t)h->nccl_comm, h->stream));
   }
   NCK(g_nccl.GroupEnd());
   if (nr > 0) {
-    LAUNCH(h, k_unpack, lvpp_grid(nr, 256, 4), 256, 0, nr, h->recv_nodes, (const double2*)h->recv_buf, (double2*)d_v);
+    LAUNCH(h, k_unpack, lvpp_grid(nr, 256, 4), 256, 0, nr, H.recv_nodes, (const double2*)H.recv_buf, (double2*)d_v);
     CK(cudaGetLastError());
   }
+  return 0;
+}
+
+int lvpp_halo_forward_impl(lvpp_problem* h, double* d_v) { return lvpp_halo_forward_level(h, h->halo, d_v); }
+
+int lvpp_halo_exchange_i32(lvpp_problem* h, const LevelHalo& H, const int32_t* d_send, int32_t* d_recv) {
+  if (h->nranks <= 1 || H.num_neighbors == 0) return 0;
+  if (!h->nccl_comm) { lvpp_set_error("communicator not initialised"); return LVPP_E_COMM; }
+  NCK(g_nccl.GroupStart());
+  for (int b = 0; b < H.num_neighbors; ++b) {
+    const int64_t s0 = H.send_ptr[b], s1 = H.send_ptr[b + 1], r0 = H.recv_ptr[b], r1 = H.recv_ptr[b + 1];
+    if (s1 > s0)
+      NCK(g_nccl.Send(d_send + s0, (size_t)(s1 - s0), ncclInt32, H.neighbor_ranks[b], (ncclComm_t)h->nccl_comm, h->stream));
+    if (r1 > r0)
+      NCK(g_nccl.Recv(d_recv + r0, (size_t)(r1 - r0), ncclInt32, H.neighbor_ranks[b], (ncclComm_t)h->nccl_comm, h->stream));
+  }
+  NCK(g_nccl.GroupEnd());
   return 0;
 }
 

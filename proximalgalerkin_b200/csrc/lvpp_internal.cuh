@@ -66,6 +66,9 @@ struct LevelHalo {
   int32_t* recv_nodes = nullptr;  // device
   double* send_buf = nullptr;     // device [2 * nsend]
   double* recv_buf = nullptr;     // device [2 * nrecv]
+  // host copies used by the multigrid setup: ghost node of every recv slot, its number on the owning
+  // rank and the neighbour slot it comes from
+  std::vector<int32_t> recv_nodes_host, ghost_owner_local, ghost_nbr;
 };
 
 // one level of the aggregation multigrid hierarchy; level 0 aliases the fine operator
@@ -89,8 +92,10 @@ struct MgLevel {
   // smoother / work vectors [2V]
   double* binv = nullptr;        // [Vown * 4] inverse of the 2x2 node block, row-major
   double *b = nullptr, *x = nullptr, *t = nullptr;
+  double* ev = nullptr;          // [2V] power-iteration vector (lambda_max of Binv J, kept between updates)
+  double omega = 0.7;            // damping of the node-block Jacobi smoother on this level
+  double lambda = 0.0;           // last estimate of lambda_max(Binv J)
   LevelHalo halo;
-  bool replicated = false;       // multi-GPU: level holds the whole (all ranks') coarse problem
 };
 
 struct lvpp_problem {
@@ -150,13 +155,7 @@ struct lvpp_problem {
   // communication
   int rank = 0, nranks = 1;
   void* nccl_comm = nullptr;
-  int num_neighbors = 0;
-  std::vector<int32_t> neighbor_ranks;
-  std::vector<int64_t> send_ptr, recv_ptr;
-  int32_t* send_nodes = nullptr;  // device
-  int32_t* recv_nodes = nullptr;  // device
-  double* send_buf = nullptr;     // device [2 * nsend]
-  double* recv_buf = nullptr;     // device [2 * nrecv]
+  LevelHalo halo;                 // fine-level halo (lvpp_obstacle_desc)
   int64_t global_rows = 0;
   // multigrid hierarchy + GMRES workspace (built lazily by lvpp_mg_setup)
   std::vector<MgLevel> levels;
@@ -164,15 +163,22 @@ struct lvpp_problem {
   double h0 = 0.0;                // node spacing used by the coordinate aggregation
   double xmin[3] = {0, 0, 0};
   int mg_nsmooth = 2;
-  double mg_omega = 0.7, mg_over = 1.0;
-  double* coarse_lu = nullptr;    // dense LU of the coarsest operator [nc * nc]
-  int32_t* coarse_piv = nullptr;
-  int coarse_n = 0;
+  // over-correction of the piecewise-constant coarse correction and relative damping of the smoother
+  // (omega_l = mg_omega * 2 / (1.15 lambda_max)); tuned on the n = 215 obstacle problem (profiles/r01_mg_scan.txt)
+  double mg_omega = 1.0, mg_over = 1.8;
+  double mg_alpha_est = -1.0;     // alpha of the last smoother eigenvalue estimate
+  double* coarse_lu = nullptr;    // dense inverse of the coarsest operator (all ranks' rows) [nc * nc]
+  int coarse_n = 0;               // global unknowns of the coarsest level
+  int64_t coarse_off = 0;         // first global coarse node of this rank
+  int32_t* coarse_gmap = nullptr; // [V coarsest] global coarse node of every local node
+  double* coarse_bg = nullptr;    // [coarse_n] gathered right-hand side
   double* gm_V = nullptr;         // GMRES basis [(restart + 1) * 2V]
   int gm_restart = 0;
   double* gm_h = nullptr;         // device [restart + 2]
   double* gm_h_host = nullptr;    // pinned
+  double* gm_part = nullptr;      // partial sums [(restart + 2) * npartials]
   int64_t vcycles = 0;
+  int64_t fine_op_launches = 0;
 };
 
 template <class T>
@@ -239,7 +245,10 @@ int lvpp_apply_jacobian(lvpp_problem* h, const double* d_v, double* d_y, const d
                         double* partials, const int* skip_flag);                    // assembly.cu
 int lvpp_reduce_partials(lvpp_problem* h, int nvals, double* d_out);  // assembly.cu
 int lvpp_allreduce_sum(lvpp_problem* h, double* d_buf, int n);       // comm.cu
-int lvpp_halo_forward_impl(lvpp_problem* h, double* d_v);            // comm.cu
+int lvpp_halo_forward_impl(lvpp_problem* h, double* d_v);            // comm.cu (fine level)
+int lvpp_halo_forward_level(lvpp_problem* h, const LevelHalo& H, double* d_v);  // comm.cu
+// packed int32 exchange over the lists of H: d_send [nsend] in send order -> d_recv [nrecv] in recv order
+int lvpp_halo_exchange_i32(lvpp_problem* h, const LevelHalo& H, const int32_t* d_send, int32_t* d_recv);  // comm.cu
 int lvpp_minres(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_newton_opts* o,
                 int32_t* its, int32_t* reason, double* rnorm);       // krylov.cu
 int lvpp_build_preconditioner(lvpp_problem* h, const lvpp_newton_opts* o);  // krylov.cu

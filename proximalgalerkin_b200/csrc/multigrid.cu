@@ -232,12 +232,15 @@ __global__ void k_prolong_add(int64_t Vown, const int32_t* __restrict__ agg, con
 }
 
 // dense coarsest operator [n x 2n] = [J_c | I], n = 2 * Vc, Dirichlet masks applied
-__global__ void k_coarse_dense(int64_t Vc, const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ rowlen,
+__global__ void k_coarse_dense(int64_t Vc, int64_t n, const int32_t* __restrict__ gmap,
+                               const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ rowlen,
                                const uint32_t* __restrict__ col, const double* __restrict__ K,
                                const double* __restrict__ M, const double* __restrict__ D,
                                const uint8_t* __restrict__ bc, double alpha, double* __restrict__ A) {
-  const int64_t n = 2 * Vc, ld = 2 * n;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vc; i += (int64_t)gridDim.x * blockDim.x) {
+  // n = global unknowns; rows of the owned nodes only (the other ranks' rows stay zero and are summed in)
+  const int64_t ld = 2 * n;
+  for (int64_t il = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; il < Vc; il += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = il, gi = gmap[il];
     const int64_t base = slice_ptr[i >> 5] + (i & 31);
     const bool rbc = bc[i] != 0;
     const int len = rowlen[i];
@@ -249,13 +252,14 @@ __global__ void k_coarse_dense(int64_t Vc, const int64_t* __restrict__ slice_ptr
       double kuu = alpha * K[idx], kup = M[idx], kpu = M[idx], kpp = -D[idx];
       if (rbc) { kuu = (j == i) ? 1.0 : 0.0; kup = 0.0; }
       if (cbc) { if (!rbc) kuu = 0.0; kpu = 0.0; }
-      A[(2 * i) * ld + 2 * j] = kuu;
-      A[(2 * i) * ld + 2 * j + 1] = kup;
-      A[(2 * i + 1) * ld + 2 * j] = kpu;
-      A[(2 * i + 1) * ld + 2 * j + 1] = kpp;
+      const int64_t gj = gmap[j];
+      A[(2 * gi) * ld + 2 * gj] = kuu;
+      A[(2 * gi) * ld + 2 * gj + 1] = kup;
+      A[(2 * gi + 1) * ld + 2 * gj] = kpu;
+      A[(2 * gi + 1) * ld + 2 * gj + 1] = kpp;
     }
-    A[(2 * i) * ld + n + 2 * i] = 1.0;
-    A[(2 * i + 1) * ld + n + 2 * i + 1] = 1.0;
+    A[(2 * gi) * ld + n + 2 * gi] = 1.0;
+    A[(2 * gi + 1) * ld + n + 2 * gi + 1] = 1.0;
   }
 }
 
@@ -326,14 +330,15 @@ __global__ void __launch_bounds__(1024) k_gauss_jordan(int n, double* __restrict
   }
 }
 
-__global__ void k_coarse_apply(int n, const double* __restrict__ inv, const double* __restrict__ b,
+// x[r] = (inv b)[row0 + r] for the nloc owned unknowns of this rank; b holds all ranks' unknowns
+__global__ void k_coarse_apply(int n, int nloc, int row0, const double* __restrict__ inv, const double* __restrict__ b,
                                double* __restrict__ x) {
   extern __shared__ double s_b[];
   for (int c = threadIdx.x; c < n; c += blockDim.x) s_b[c] = b[c];
   __syncthreads();
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nloc; r += gridDim.x * blockDim.x) {
     double s = 0.0;
-    for (int c = 0; c < n; ++c) s += inv[(int64_t)c * n + r] * s_b[c];
+    for (int c = 0; c < n; ++c) s += inv[(int64_t)c * n + row0 + r] * s_b[c];
     x[r] = s;
   }
 }
@@ -424,15 +429,130 @@ __global__ void __launch_bounds__(256) k_reduce_multi(int nparts, int nvals, con
 
 // ------------------------------------------------------------------------------------------------
 // hierarchy construction
+static int reduce_to_host(lvpp_problem* h, double* partials, int nvals, double* dst_dev, double* dst_host);
+
+// sum over ranks of a few host doubles (setup only)
+static int host_allreduce_sum(lvpp_problem* h, double* vals, int n) {
+  if (h->nranks <= 1) return 0;
+  if (n > 64) { lvpp_set_error("host_allreduce_sum: too many values"); return LVPP_E_INVALID; }
+  CK(cudaMemcpyAsync(h->gm_h, vals, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  CKR(lvpp_allreduce_sum(h, h->gm_h, n));
+  CK(cudaMemcpyAsync(vals, h->gm_h, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+__global__ void k_pack_agg(int64_t n, const int32_t* __restrict__ nodes, const int32_t* __restrict__ agg,
+                           const uint8_t* __restrict__ bc, int32_t* __restrict__ out) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t i = nodes[p];
+    out[p] = (int32_t)((uint32_t)agg[i] | (bc[i] ? 0x80000000u : 0u));
+  }
+}
+__global__ void k_scatter_i32(int64_t n, const int32_t* __restrict__ nodes, const int32_t* __restrict__ vals,
+                              int32_t* __restrict__ dst) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
+    dst[nodes[p]] = vals[p];
+}
+__global__ void k_ev_init(int64_t Vown, double2* __restrict__ v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vown; i += (int64_t)gridDim.x * blockDim.x) {
+    // fixed pseudo-random start vector (integer hash of the node number)
+    uint32_t a = (uint32_t)i * 2654435761u + 12345u;
+    a ^= a >> 15; a *= 2246822519u; a ^= a >> 13;
+    uint32_t b = a * 3266489917u + 1u;
+    b ^= b >> 16;
+    v[i] = make_double2((double)(a & 0xffff) / 65536.0 - 0.5, (double)(b & 0xffff) / 65536.0 - 0.5);
+  }
+}
+
 static int level_alloc_vectors(lvpp_problem* h, MgLevel& L) {
   CKR(lvpp_dalloc(h, &L.binv, (size_t)4 * L.Vown));
   CKR(lvpp_dalloc(h, &L.b, (size_t)2 * L.V));
   CKR(lvpp_dalloc(h, &L.x, (size_t)2 * L.V));
   CKR(lvpp_dalloc(h, &L.t, (size_t)2 * L.V));
+  CKR(lvpp_dalloc(h, &L.ev, (size_t)2 * L.V));
   return 0;
 }
 
-// builds level l + 1 from level l (single rank or replicated levels: no ghosts)
+// Coarse halo of level l + 1 from the aggregates of level l: the owner sends the aggregate number (and
+// Dirichlet bit) of every node on its send lists; both sides take the sorted unique aggregate numbers
+// per neighbour, so the coarse send list of the owner and the coarse recv list of the receiver agree
+// entry by entry.  Coarse ghosts are numbered after the owned coarse nodes, neighbour by neighbour.
+static int build_coarse_halo(lvpp_problem* h, MgLevel& F, MgLevel& C, int64_t Vc) {
+  const LevelHalo& FH = F.halo;
+  LevelHalo& CH = C.halo;
+  C.Vown = Vc;
+  C.V = Vc;
+  if (h->nranks <= 1 || FH.num_neighbors == 0) return 0;
+  const int64_t ns = FH.send_ptr.back(), nr = FH.recv_ptr.back();
+  int32_t *d_s = nullptr, *d_r = nullptr;
+  CKR(lvpp_dalloc(h, &d_s, (size_t)ns, false));
+  CKR(lvpp_dalloc(h, &d_r, (size_t)nr, false));
+  if (ns > 0) {
+    LAUNCH(h, k_pack_agg, lvpp_grid(ns, 256, 4), 256, 0, ns, FH.send_nodes, F.agg, F.bc_flag, d_s);
+    CK(cudaGetLastError());
+  }
+  CKR(lvpp_halo_exchange_i32(h, FH, d_s, d_r));
+  std::vector<uint32_t> hs((size_t)ns), hr((size_t)nr);
+  CK(cudaMemcpyAsync(hs.data(), d_s, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(hr.data(), d_r, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CH.num_neighbors = FH.num_neighbors;
+  CH.neighbor_ranks = FH.neighbor_ranks;
+  CH.send_ptr.assign(1, 0);
+  CH.recv_ptr.assign(1, 0);
+  std::vector<int32_t> csend, crecv, aggghost((size_t)nr);
+  std::vector<uint8_t> cbcg;
+  int64_t ncg = 0;
+  for (int b = 0; b < FH.num_neighbors; ++b) {
+    std::vector<uint32_t> u;
+    for (int64_t p = FH.send_ptr[b]; p < FH.send_ptr[b + 1]; ++p) u.push_back(hs[p] & 0x7fffffffu);
+    std::sort(u.begin(), u.end());
+    u.erase(std::unique(u.begin(), u.end()), u.end());
+    for (uint32_t v : u) csend.push_back((int32_t)v);
+    CH.send_ptr.push_back((int64_t)csend.size());
+    std::vector<uint32_t> w;
+    for (int64_t p = FH.recv_ptr[b]; p < FH.recv_ptr[b + 1]; ++p) w.push_back(hr[p] & 0x7fffffffu);
+    std::sort(w.begin(), w.end());
+    w.erase(std::unique(w.begin(), w.end()), w.end());
+    cbcg.resize((size_t)(ncg + (int64_t)w.size()), 0);
+    for (int64_t p = FH.recv_ptr[b]; p < FH.recv_ptr[b + 1]; ++p) {
+      const int64_t id = std::lower_bound(w.begin(), w.end(), hr[p] & 0x7fffffffu) - w.begin();
+      aggghost[p] = (int32_t)(Vc + ncg + id);
+      cbcg[ncg + id] = (uint8_t)(hr[p] >> 31);
+    }
+    for (size_t id = 0; id < w.size(); ++id) {
+      crecv.push_back((int32_t)(Vc + ncg + (int64_t)id));
+      CH.ghost_owner_local.push_back((int32_t)w[id]);
+      CH.ghost_nbr.push_back(b);
+    }
+    ncg += (int64_t)w.size();
+    CH.recv_ptr.push_back(ncg);
+  }
+  CH.recv_nodes_host = crecv;
+  C.V = Vc + ncg;
+  CKR(lvpp_dalloc(h, &CH.send_nodes, csend.size(), false));
+  CKR(lvpp_dalloc(h, &CH.recv_nodes, crecv.size(), false));
+  CKR(lvpp_dalloc(h, &CH.send_buf, 2 * csend.size()));
+  CKR(lvpp_dalloc(h, &CH.recv_buf, 2 * crecv.size()));
+  int32_t* d_ag = nullptr;
+  CKR(lvpp_dalloc(h, &d_ag, (size_t)nr, false));
+  if (!csend.empty()) CK(cudaMemcpyAsync(CH.send_nodes, csend.data(), sizeof(int32_t) * csend.size(), cudaMemcpyHostToDevice, h->stream));
+  if (!crecv.empty()) CK(cudaMemcpyAsync(CH.recv_nodes, crecv.data(), sizeof(int32_t) * crecv.size(), cudaMemcpyHostToDevice, h->stream));
+  if (nr > 0) {
+    CK(cudaMemcpyAsync(d_ag, aggghost.data(), sizeof(int32_t) * nr, cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(h, k_scatter_i32, lvpp_grid(nr, 256, 4), 256, 0, nr, FH.recv_nodes, d_ag, F.agg);
+    CK(cudaGetLastError());
+  }
+  if (ncg > 0) CK(cudaMemcpyAsync(C.bc_flag + Vc, cbcg.data(), (size_t)ncg, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CKR(lvpp_dfree(h, d_s));
+  CKR(lvpp_dfree(h, d_r));
+  CKR(lvpp_dfree(h, d_ag));
+  return 0;
+}
+
+// builds level l + 1 from level l; every rank aggregates its owned nodes only
 static int build_next_level(lvpp_problem* h, int l, bool* stop) {
   MgLevel& F = h->levels[l];
   *stop = false;
@@ -463,23 +583,25 @@ static int build_next_level(lvpp_problem* h, int l, bool* stop) {
   int64_t Vc = 0;
   CK(cudaMemcpyAsync(&Vc, scan + (n - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  if (Vc >= n || (double)Vc > 0.75 * (double)n) {  // no useful coarsening
+  double tot[2] = {(double)Vc, (double)n};
+  CKR(host_allreduce_sum(h, tot, 2));  // the decision is collective
+  if (tot[0] >= tot[1] || tot[0] > 0.75 * tot[1]) {  // no useful coarsening
     *stop = true;
     for (void* p : {(void*)keys, (void*)skeys, (void*)vals, (void*)svals, (void*)scan, tmp, stmp}) CKR(lvpp_dfree(h, p));
     return 0;
   }
   MgLevel C;
-  C.V = C.Vown = Vc;
   CKR(lvpp_dalloc(h, &F.agg, (size_t)F.V));
   CKR(lvpp_dalloc(h, &F.agg_members, (size_t)n, false));
   CKR(lvpp_dalloc(h, &F.agg_ptr, (size_t)Vc + 1));
   CKR(lvpp_dalloc(h, &C.box, (size_t)3 * Vc));
-  CKR(lvpp_dalloc(h, &C.bc_flag, (size_t)Vc));
+  CKR(lvpp_dalloc(h, &C.bc_flag, (size_t)(Vc + (F.V - F.Vown))));  // coarse ghosts <= fine ghosts
   LAUNCH(h, k_agg_fill, lvpp_grid(n, 256, 16), 256, 0, n, skeys, svals, scan, F.agg, F.agg_members, F.agg_ptr,
          C.box, C.bc_flag);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   for (void* p : {(void*)keys, (void*)skeys, (void*)vals, (void*)svals, (void*)scan, tmp, stmp}) CKR(lvpp_dfree(h, p));
+  CKR(build_coarse_halo(h, F, C, Vc));
 
   // ---- coarse pattern and the Galerkin slot map: sort every fine slot by (coarse row, coarse col)
   const int64_t S = F.slots;
@@ -564,14 +686,46 @@ static int build_next_level(lvpp_problem* h, int l, bool* stop) {
   return 0;
 }
 
+static double env_double(const char* name, double dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atof(v) : dflt;
+}
+
 int lvpp_mg_setup(lvpp_problem* h) {
   if (h->mg_ready) return 0;
-  if (h->nranks > 1) { lvpp_set_error("multigrid preconditioner: multi-GPU hierarchy not built"); return LVPP_E_INVALID; }
+  if (h->nranks > 64) { lvpp_set_error("multigrid preconditioner: more than 64 ranks"); return LVPP_E_INVALID; }
+  // tunables (defaults are the tested values)
+  h->mg_over = env_double("LVPP_MG_OVER", h->mg_over);
+  h->mg_omega = env_double("LVPP_MG_OMEGA", h->mg_omega);
+  h->mg_nsmooth = (int)env_double("LVPP_MG_NSMOOTH", h->mg_nsmooth);
+  // GMRES workspace (also the scratch of the collective decisions below)
+  h->gm_restart = (int)env_double("LVPP_GMRES_RESTART", 50);
+  if (h->gm_restart < 2 || h->gm_restart > 200) { lvpp_set_error("bad LVPP_GMRES_RESTART"); return LVPP_E_INVALID; }
+  CKR(lvpp_dalloc(h, &h->gm_V, (size_t)(h->gm_restart + 1) * 2 * h->V));
+  CKR(lvpp_dalloc(h, &h->gm_h, (size_t)h->gm_restart + 72));
+  CKR(lvpp_dalloc(h, &h->gm_part, (size_t)(h->gm_restart + 2) * h->npartials));
+  CK(cudaMallocHost((void**)&h->gm_h_host, sizeof(double) * (h->gm_restart + 72)));
   h->levels.clear();
   MgLevel L0;
   L0.V = h->V; L0.Vown = h->Vown; L0.nslices = h->nslices; L0.slots = h->sell_slots; L0.nnz = h->scalar_nnz;
   L0.slice_ptr = h->slice_ptr; L0.col = h->col; L0.rowlen = h->rowlen; L0.diag_k = h->diag_k;
   L0.K = h->K; L0.M = h->M; L0.D = h->D; L0.bc_flag = h->bc_flag;
+  L0.halo = h->halo;
+  if (h->nranks > 1 && L0.halo.num_neighbors > 0) {
+    // number of every ghost node on its owner (needed when the fine level is also the coarsest)
+    LevelHalo& H = L0.halo;
+    const int64_t nr = H.recv_ptr.back();
+    int32_t* d_r = nullptr;
+    CKR(lvpp_dalloc(h, &d_r, (size_t)nr, false));
+    CKR(lvpp_halo_exchange_i32(h, H, H.send_nodes, d_r));
+    H.ghost_owner_local.resize((size_t)nr);
+    H.ghost_nbr.resize((size_t)nr);
+    CK(cudaMemcpyAsync(H.ghost_owner_local.data(), d_r, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int b = 0; b < H.num_neighbors; ++b)
+      for (int64_t p = H.recv_ptr[b]; p < H.recv_ptr[b + 1]; ++p) H.ghost_nbr[p] = b;
+    CKR(lvpp_dfree(h, d_r));
+  }
   CKR(lvpp_dalloc(h, &L0.box, (size_t)3 * L0.Vown));
   LAUNCH(h, k_box0, lvpp_grid(L0.Vown, 256, 16), 256, 0, L0.Vown, h->tdim, h->coords, h->xmin[0], h->xmin[1],
          h->xmin[2], 1.0 / h->h0, L0.box);
@@ -579,29 +733,111 @@ int lvpp_mg_setup(lvpp_problem* h) {
   CKR(level_alloc_vectors(h, L0));
   h->levels.push_back(L0);
   for (int l = 0; l < MG_MAX_LEVELS - 1; ++l) {
-    if (h->levels[l].Vown <= MG_COARSE_TARGET) break;
+    double tot = (double)h->levels[l].Vown;
+    CKR(host_allreduce_sum(h, &tot, 1));
+    if (tot <= (double)MG_COARSE_TARGET) break;
     bool stop = false;
     CKR(build_next_level(h, l, &stop));
     if (stop) break;
   }
+  // coarsest level: global numbering of all ranks' coarse nodes, rank by rank
   const MgLevel& Lc = h->levels.back();
-  if (Lc.Vown > MG_COARSE_MAX) {
-    lvpp_set_error("multigrid: coarsening stalled at %lld nodes (limit %d)", (long long)Lc.Vown, MG_COARSE_MAX);
+  std::vector<double> cnt((size_t)h->nranks, 0.0);
+  cnt[h->rank] = (double)Lc.Vown;
+  CKR(host_allreduce_sum(h, cnt.data(), h->nranks));
+  std::vector<int64_t> off((size_t)h->nranks + 1, 0);
+  for (int r = 0; r < h->nranks; ++r) off[r + 1] = off[r] + (int64_t)(cnt[r] + 0.5);
+  if (off[h->nranks] > MG_COARSE_MAX) {
+    lvpp_set_error("multigrid: coarsening stalled at %lld nodes (limit %d)", (long long)off[h->nranks], MG_COARSE_MAX);
     return LVPP_E_CAPACITY;
   }
-  h->coarse_n = (int)(2 * Lc.Vown);
+  h->coarse_n = (int)(2 * off[h->nranks]);
+  h->coarse_off = off[h->rank];
+  {
+    std::vector<int32_t> gmap((size_t)Lc.V, -1);
+    for (int64_t i = 0; i < Lc.Vown; ++i) gmap[i] = (int32_t)(h->coarse_off + i);
+    const LevelHalo& H = Lc.halo;
+    for (size_t p = 0; p < H.recv_nodes_host.size() && h->nranks > 1; ++p)
+      gmap[H.recv_nodes_host[p]] = (int32_t)(off[H.neighbor_ranks[H.ghost_nbr[p]]] + H.ghost_owner_local[p]);
+    for (int64_t i = 0; i < Lc.V; ++i)
+      if (gmap[i] < 0) { lvpp_set_error("multigrid: ghost node %lld of the coarsest level has no owner", (long long)i); return LVPP_E_INVALID; }
+    CKR(lvpp_dalloc(h, &h->coarse_gmap, (size_t)Lc.V, false));
+    CK(cudaMemcpyAsync(h->coarse_gmap, gmap.data(), sizeof(int32_t) * Lc.V, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
   CKR(lvpp_dalloc(h, &h->coarse_lu, (size_t)h->coarse_n * h->coarse_n));
-  // GMRES workspace
-  h->gm_restart = 40;
-  CKR(lvpp_dalloc(h, &h->gm_V, (size_t)(h->gm_restart + 1) * 2 * h->V));
-  CKR(lvpp_dalloc(h, &h->gm_h, (size_t)h->gm_restart + 8));
-  CK(cudaMallocHost((void**)&h->gm_h_host, sizeof(double) * (h->gm_restart + 8)));
+  CKR(lvpp_dalloc(h, &h->coarse_bg, (size_t)h->coarse_n));
   CK(cudaStreamSynchronize(h->stream));
+  if (getenv("LVPP_MG_VERBOSE") && h->rank == 0) {
+    fprintf(stderr, "[lvpp mg] %d levels:", (int)h->levels.size());
+    for (const MgLevel& L : h->levels) fprintf(stderr, " %lld(+%lld)", (long long)L.Vown, (long long)(L.V - L.Vown));
+    fprintf(stderr, "; coarsest dense n = %d\n", h->coarse_n);
+  }
   h->mg_ready = true;
   return 0;
 }
 
-// per Newton step: coarse D, node-block inverses, dense inverse of the coarsest operator
+static int level_op_local(lvpp_problem* h, MgLevel& L, int epi, double omega, const double* v, const double* b,
+                         double* y) {
+  OpArgs p = lvpp_level_op(h, L);
+  p.v = (const double2*)v;
+  p.y = (double2*)y;
+  p.epi = epi;
+  p.b = (const double2*)b;
+  p.binv = L.binv;
+  p.omega = omega;
+  const int grid = lvpp_grid(L.Vown, 256, 6);
+  if (&L == &h->levels[0]) h->fine_op_launches++;
+  LAUNCH(h, k_block_op<0>, grid, 256, 0, p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ghost update of v, then the operator
+static int level_op(lvpp_problem* h, MgLevel& L, int epi, double omega, const double* v, const double* b, double* y) {
+  if (h->nranks > 1) CKR(lvpp_halo_forward_level(h, L.halo, const_cast<double*>(v)));
+  return level_op_local(h, L, epi, omega, v, b, y);
+}
+
+static int build_binv(lvpp_problem* h, MgLevel& L, double omega) {
+  LAUNCH(h, k_build_binv, lvpp_grid(L.Vown, 256, 8), 256, 0, L.Vown, L.slice_ptr, L.diag_k, L.K, L.M, L.D,
+         L.bc_flag, h->alpha, omega, L.binv);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// lambda_max(Binv J) of one level by power iteration on I + Binv J (the Jacobi epilogue with b = 0 and
+// omega = -1) from a fixed start vector: the estimate depends only on the operator, never on history
+static int estimate_lambda(lvpp_problem* h, MgLevel& L) {
+  const int nb = h->npartials;
+  const int nit = 10;
+  LAUNCH(h, k_ev_init, lvpp_grid(L.Vown, 256, 8), 256, 0, L.Vown, (double2*)L.ev);
+  CK(cudaGetLastError());
+  CK(cudaMemsetAsync(L.x, 0, sizeof(double) * 2 * L.V, h->stream));
+  double lam = 0.0;
+  for (int it = 0; it <= nit; ++it) {
+    // normalise ev, then t = ev + Binv J ev
+    LAUNCH(h, k_multi_dot, nb, 256, 0, L.Vown, (const double2*)L.ev, L.V, 0, 1, (const double2*)L.ev, nb, h->gm_part);
+    CK(cudaGetLastError());
+    CKR(reduce_to_host(h, h->gm_part, 1, h->gm_h, h->gm_h_host));
+    const double nrm = sqrt(h->gm_h_host[0]);
+    if (!(nrm > 0.0) || !std::isfinite(nrm)) { lvpp_set_error("multigrid: eigenvalue estimate failed"); return LVPP_E_INVALID; }
+    if (it > 0) lam = nrm - 1.0;  // ||(I + Binv J) ev|| with ||ev|| = 1
+    if (it == nit) {
+      LAUNCH(h, k_axpby, nb, 256, 0, L.Vown, 1.0 / nrm, (const double2*)L.ev, 0, (double2*)L.ev);
+      CK(cudaGetLastError());
+      break;
+    }
+    LAUNCH(h, k_axpby, nb, 256, 0, L.Vown, 1.0 / nrm, (const double2*)L.ev, 0, (double2*)L.ev);
+    CK(cudaGetLastError());
+    CKR(level_op(h, L, EPI_JACOBI, -1.0, L.ev, L.x, L.t));
+    std::swap(L.ev, L.t);
+  }
+  L.lambda = lam;
+  return 0;
+}
+
+// per Newton step: coarse D, damping, node-block inverses, dense inverse of the coarsest operator
 int lvpp_mg_update(lvpp_problem* h) {
   CKR(lvpp_mg_setup(h));
   const int nl = (int)h->levels.size();
@@ -611,11 +847,23 @@ int lvpp_mg_update(lvpp_problem* h) {
     LAUNCH(h, k_galerkin, lvpp_grid(C.nnz, 256, 16), 256, 0, C.nnz, F.gal_ptr, F.gal_src, F.gal_dst, 1, F.D, F.D, C.D, C.D);
     CK(cudaGetLastError());
   }
-  for (int l = 0; l < nl; ++l) {
+  // Damping: lambda_max(Binv J) is set by the stiffness block (mesh and element, not psi), so it is estimated
+  // when alpha changes (once per proximal step) with a 15 % margin for its drift over the Newton steps.
+  const bool estimate = !(h->mg_alpha_est == h->alpha);
+  for (int l = 0; l + 1 < nl; ++l) {
     MgLevel& L = h->levels[l];
-    LAUNCH(h, k_build_binv, lvpp_grid(L.Vown, 256, 8), 256, 0, L.Vown, L.slice_ptr, L.diag_k, L.K, L.M, L.D,
-           L.bc_flag, h->alpha, h->mg_omega, L.binv);
-    CK(cudaGetLastError());
+    if (estimate) {
+      CKR(build_binv(h, L, 1.0));
+      CKR(estimate_lambda(h, L));
+      L.omega = h->mg_omega * std::min(1.0, 2.0 / (1.15 * L.lambda));
+    }
+    CKR(build_binv(h, L, L.omega));
+  }
+  h->mg_alpha_est = h->alpha;
+  if (estimate && getenv("LVPP_MG_VERBOSE") && h->rank == 0) {
+    fprintf(stderr, "[lvpp mg] lambda_max / omega:");
+    for (int l = 0; l + 1 < nl; ++l) fprintf(stderr, " %.3f/%.3f", h->levels[l].lambda, h->levels[l].omega);
+    fprintf(stderr, "\n");
   }
   MgLevel& Lc = h->levels.back();
   const int n = h->coarse_n;
@@ -623,8 +871,14 @@ int lvpp_mg_update(lvpp_problem* h) {
   int* d_err = nullptr;
   CKR(lvpp_dalloc(h, &aug, (size_t)n * 2 * n));
   CKR(lvpp_dalloc(h, &d_err, 1));
-  LAUNCH(h, k_coarse_dense, lvpp_grid(Lc.Vown, 128, 4), 128, 0, Lc.Vown, Lc.slice_ptr, Lc.rowlen, Lc.col, Lc.K, Lc.M,
-         Lc.D, Lc.bc_flag, h->alpha, aug);
+  LAUNCH(h, k_coarse_dense, lvpp_grid(Lc.Vown, 128, 4), 128, 0, Lc.Vown, n, h->coarse_gmap, Lc.slice_ptr, Lc.rowlen,
+         Lc.col, Lc.K, Lc.M, Lc.D, Lc.bc_flag, h->alpha, aug);
+  CK(cudaGetLastError());
+  if (h->nranks > 1) {  // every rank holds the whole coarsest operator and inverts it redundantly
+    const size_t total = (size_t)n * 2 * n;
+    for (size_t o = 0; o < total; o += (size_t)1 << 30)
+      CKR(lvpp_allreduce_sum(h, aug + o, (int)std::min<size_t>((size_t)1 << 30, total - o)));
+  }
   LAUNCH(h, k_gauss_jordan, 1, 1024, 0, n, aug, h->coarse_lu, d_err);
   CK(cudaGetLastError());
   int herr = 0;
@@ -636,21 +890,7 @@ int lvpp_mg_update(lvpp_problem* h) {
   return 0;
 }
 
-static int level_op(lvpp_problem* h, MgLevel& L, int epi, const double* v, const double* b, double* y) {
-  OpArgs p = lvpp_level_op(h, L);
-  p.v = (const double2*)v;
-  p.y = (double2*)y;
-  p.epi = epi;
-  p.b = (const double2*)b;
-  p.binv = L.binv;
-  p.omega = h->mg_omega;
-  const int grid = lvpp_grid(L.Vown, 256, 6);
-  LAUNCH(h, k_block_op<0>, grid, 256, 0, p);
-  CK(cudaGetLastError());
-  return 0;
-}
-
-// z = V-cycle(b) with zero initial guess on level 0; returns the buffer that holds z
+// z = V-cycle(b) with zero initial guess on level 0; returns the buffer that holds z (owned entries)
 int lvpp_mg_vcycle(lvpp_problem* h, const double* b_in, double** z_out) {
   const int nl = (int)h->levels.size();
   std::vector<double*> cur(nl), oth(nl);
@@ -660,25 +900,35 @@ int lvpp_mg_vcycle(lvpp_problem* h, const double* b_in, double** z_out) {
   for (int l = 0; l < nl - 1; ++l) {
     MgLevel& L = h->levels[l];
     cur[l] = L.x; oth[l] = L.t;
-    LAUNCH(h, k_smooth_first, lvpp_grid(L.Vown, 256, 6), 256, 0, L.Vown, (const double2*)rhs[l], L.binv, h->mg_omega,
+    LAUNCH(h, k_smooth_first, lvpp_grid(L.Vown, 256, 6), 256, 0, L.Vown, (const double2*)rhs[l], L.binv, L.omega,
            (double2*)cur[l]);
     CK(cudaGetLastError());
     for (int s = 1; s < nsm; ++s) {
-      CKR(level_op(h, L, EPI_JACOBI, cur[l], rhs[l], oth[l]));
+      CKR(level_op(h, L, EPI_JACOBI, L.omega, cur[l], rhs[l], oth[l]));
       std::swap(cur[l], oth[l]);
     }
-    CKR(level_op(h, L, EPI_RESID, cur[l], rhs[l], oth[l]));  // residual into the spare buffer
+    CKR(level_op(h, L, EPI_RESID, L.omega, cur[l], rhs[l], oth[l]));  // residual into the spare buffer
     MgLevel& C = h->levels[l + 1];
     LAUNCH(h, k_restrict, lvpp_grid(C.Vown, 256, 6), 256, 0, C.Vown, L.agg_ptr, L.agg_members, (const double2*)oth[l],
            C.bc_flag, (double2*)C.b);
     CK(cudaGetLastError());
     rhs[l + 1] = C.b;
   }
-  {  // coarsest: x = inv * b
+  {  // coarsest: gather the right-hand side of all ranks, x = inv * b for the owned unknowns
     MgLevel& L = h->levels[nl - 1];
     cur[nl - 1] = L.x; oth[nl - 1] = L.t;
     const int n = h->coarse_n;
-    LAUNCH(h, k_coarse_apply, (n + 127) / 128, 128, sizeof(double) * n, n, h->coarse_lu, rhs[nl - 1], cur[nl - 1]);
+    const double* bg = rhs[nl - 1];
+    if (h->nranks > 1) {
+      CK(cudaMemsetAsync(h->coarse_bg, 0, sizeof(double) * n, h->stream));
+      CK(cudaMemcpyAsync(h->coarse_bg + 2 * h->coarse_off, rhs[nl - 1], sizeof(double) * 2 * L.Vown,
+                         cudaMemcpyDeviceToDevice, h->stream));
+      CKR(lvpp_allreduce_sum(h, h->coarse_bg, n));
+      bg = h->coarse_bg;
+    }
+    const int nloc = (int)(2 * L.Vown);
+    LAUNCH(h, k_coarse_apply, (nloc + 127) / 128, 128, sizeof(double) * n, n, nloc, (int)(2 * h->coarse_off), h->coarse_lu,
+           bg, cur[nl - 1]);
     CK(cudaGetLastError());
   }
   for (int l = nl - 2; l >= 0; --l) {
@@ -687,7 +937,7 @@ int lvpp_mg_vcycle(lvpp_problem* h, const double* b_in, double** z_out) {
            h->mg_over, (double2*)cur[l]);
     CK(cudaGetLastError());
     for (int s = 0; s < nsm; ++s) {
-      CKR(level_op(h, L, EPI_JACOBI, cur[l], rhs[l], oth[l]));
+      CKR(level_op(h, L, EPI_JACOBI, L.omega, cur[l], rhs[l], oth[l]));
       std::swap(cur[l], oth[l]);
     }
   }
@@ -713,8 +963,7 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
   const int64_t Vown = h->Vown, stride2 = h->V;  // basis vectors are 2V doubles = V double2
   const int nb = h->npartials;
   double2* Vb = (double2*)h->gm_V;
-  double* gpart = nullptr;  // partial sums [(m + 2) * nb]
-  CKR(lvpp_dalloc(h, &gpart, (size_t)(m + 2) * nb));
+  double* gpart = h->gm_part;  // partial sums [(m + 2) * nb]
   const int maxit = o->ksp_max_it > 0 ? o->ksp_max_it : 1000;
   CK(cudaEventRecord(h->ev0, h->stream));
   std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), yv(m);
@@ -729,8 +978,7 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
     if (first) {
       CK(cudaMemcpyAsync(vec(0), d_rhs, sizeof(double) * 2 * Vown, cudaMemcpyDeviceToDevice, h->stream));
     } else {
-      if (h->nranks > 1) CKR(lvpp_halo_forward_impl(h, d_y));
-      CKR(level_op(h, L0, EPI_RESID, d_y, d_rhs, vec(0)));
+      CKR(level_op(h, L0, EPI_RESID, 1.0, d_y, d_rhs, vec(0)));
     }
     LAUNCH(h, k_multi_dot, nb, 256, 0, Vown, Vb, stride2, 0, 1, (const double2*)vec(0), nb, gpart);
     CK(cudaGetLastError());
@@ -752,9 +1000,9 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
       // w = J M^-1 v_j  -> stored in v_{j+1}
       double* z = nullptr;
       CKR(lvpp_mg_vcycle(h, vec(j), &z));
-      if (h->nranks > 1) CKR(lvpp_halo_forward_impl(h, z));
+      if (h->nranks > 1) CKR(lvpp_halo_forward_level(h, L0.halo, z));
       CK(cudaEventRecord(h->evs0, h->stream));
-      CKR(level_op(h, L0, EPI_NONE, z, nullptr, vec(j + 1)));
+      CKR(level_op_local(h, L0, EPI_NONE, 1.0, z, nullptr, vec(j + 1)));
       CK(cudaEventRecord(h->evs1, h->stream));
       double* hcol = &H[(size_t)j * (m + 1)];
       for (int k = 0; k <= j + 1; ++k) hcol[k] = 0.0;
@@ -836,7 +1084,6 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
   CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->t_krylov_ms += ms;
   h->krylov_its += total;
-  CKR(lvpp_dfree(h, gpart));
   if (its_out) *its_out = total;
   if (reason_out) *reason_out = reason;
   if (rnorm_out) *rnorm_out = rnorm;

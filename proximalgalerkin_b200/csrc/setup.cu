@@ -373,21 +373,27 @@ extern "C" int lvpp_create(const lvpp_obstacle_desc* d, lvpp_handle* out) {
       if (dv) CKR(lvpp_dfree(h, dv));
     }
     // halo lists
-    h->num_neighbors = d->num_neighbors;
+    LevelHalo& H = h->halo;
+    H.num_neighbors = d->num_neighbors;
     if (d->num_neighbors > 0) {
       if (!d->neighbor_ranks || !d->send_ptr || !d->recv_ptr || !d->send_nodes || !d->recv_nodes) {
         lvpp_set_error("null halo array"); return LVPP_E_INVALID;
       }
-      h->neighbor_ranks.assign(d->neighbor_ranks, d->neighbor_ranks + d->num_neighbors);
-      h->send_ptr.assign(d->send_ptr, d->send_ptr + d->num_neighbors + 1);
-      h->recv_ptr.assign(d->recv_ptr, d->recv_ptr + d->num_neighbors + 1);
-      const int64_t ns = h->send_ptr.back(), nr = h->recv_ptr.back();
-      CKR(lvpp_dalloc(h, &h->send_nodes, (size_t)ns, false));
-      CKR(lvpp_dalloc(h, &h->recv_nodes, (size_t)nr, false));
-      CK(cudaMemcpy(h->send_nodes, d->send_nodes, sizeof(int32_t) * ns, cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(h->recv_nodes, d->recv_nodes, sizeof(int32_t) * nr, cudaMemcpyHostToDevice));
-      CKR(lvpp_dalloc(h, &h->send_buf, (size_t)2 * ns));
-      CKR(lvpp_dalloc(h, &h->recv_buf, (size_t)2 * nr));
+      H.neighbor_ranks.assign(d->neighbor_ranks, d->neighbor_ranks + d->num_neighbors);
+      H.send_ptr.assign(d->send_ptr, d->send_ptr + d->num_neighbors + 1);
+      H.recv_ptr.assign(d->recv_ptr, d->recv_ptr + d->num_neighbors + 1);
+      const int64_t ns = H.send_ptr.back(), nr = H.recv_ptr.back();
+      for (int64_t p = 0; p < ns; ++p)
+        if (d->send_nodes[p] < 0 || d->send_nodes[p] >= h->Vown) { lvpp_set_error("send node is not owned"); return LVPP_E_INVALID; }
+      for (int64_t p = 0; p < nr; ++p)
+        if (d->recv_nodes[p] < h->Vown || d->recv_nodes[p] >= h->V) { lvpp_set_error("recv node is not a ghost"); return LVPP_E_INVALID; }
+      H.recv_nodes_host.assign(d->recv_nodes, d->recv_nodes + nr);
+      CKR(lvpp_dalloc(h, &H.send_nodes, (size_t)ns, false));
+      CKR(lvpp_dalloc(h, &H.recv_nodes, (size_t)nr, false));
+      CK(cudaMemcpy(H.send_nodes, d->send_nodes, sizeof(int32_t) * ns, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(H.recv_nodes, d->recv_nodes, sizeof(int32_t) * nr, cudaMemcpyHostToDevice));
+      CKR(lvpp_dalloc(h, &H.send_buf, (size_t)2 * ns));
+      CKR(lvpp_dalloc(h, &H.recv_buf, (size_t)2 * nr));
     }
     CK(cudaStreamSynchronize(h->stream));
     {  // node spacing and origin for the coordinate aggregation of the multigrid hierarchy
@@ -488,6 +494,10 @@ extern "C" int lvpp_get_stats(lvpp_handle h, lvpp_stats* s) {
   s->last_spmv_ms = h->last_spmv_ms;
   s->spmv_sampled_ms = h->spmv_sampled_ms;
   s->spmv_samples = h->spmv_samples;
+  s->fine_op_launches = h->fine_op_launches;
+  s->vcycles = h->vcycles;
+  s->mg_levels = (int32_t)h->levels.size();
+  s->reserved0 = 0;
   return LVPP_OK;
 }
 

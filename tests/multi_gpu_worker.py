@@ -24,7 +24,8 @@ def main():
     make = lvpp.mesh.create_box if len(shape) == 3 else lvpp.mesh.create_rectangle
     msh = make(*shape, rank=rank, nranks=world)
     whole = make(*shape)
-    s = lvpp.obstacle_pg.setup(msh, 1)
+    popts = {"ksp_type": "gmres", "pc_type": "mg"} if len(sys.argv) > 2 and sys.argv[2] == "mg" else None
+    s = lvpp.obstacle_pg.setup(msh, 1, petsc_options=popts)
     dev = s["problem"].device_problem
     nown = msh.num_owned_vertices
     gv = msh.global_vertex
@@ -50,7 +51,7 @@ def main():
     obs = dev.observables(X)
     ok = True
     if rank == 0:
-        s1 = lvpp.obstacle_pg.setup(whole, 1)
+        s1 = lvpp.obstacle_pg.setup(whole, 1, petsc_options=popts)
         d1 = s1["problem"].device_problem
         d1.set_alpha(alpha)
         d1.set_previous(xkg)
@@ -90,7 +91,7 @@ def main():
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t)
     if rank == 0:
-        print(f"MULTI_GPU_OK world={world} shape={shape} newton={st.history['newton_steps']} u_err={err:.2e}")
+        print(f"MULTI_GPU_OK world={world} shape={shape} pc={'mg' if popts else 'jacobi'} krylov={dev.stats()['krylov_iterations']} newton={st.history['newton_steps']} u_err={err:.2e}")
     dist.destroy_process_group()
 
 
