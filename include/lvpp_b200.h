@@ -109,7 +109,14 @@ typedef struct lvpp_newton_opts {
   int32_t ksp_max_it;
   int32_t pc_type;    /* LVPP_PC_* */
   int32_t pc_degree;  /* LVPP_PC_MG: smoothing sweeps before and after the coarse correction (0 = 2) */
+  int32_t snes_linesearch; /* LVPP_LINESEARCH_*: "none"/"basic" (obstacle_pg.py:136) or PETSc's default "bt"
+                              (examples/04_multiphase/multiphase_dolfinx.py:128-143 sets none); lvpp_form_* only */
+  int32_t ksp_restart;     /* GMRES restart length of the lvpp_form_* solver (0 = 200) */
 } lvpp_newton_opts;
+
+#define LVPP_LINESEARCH_NONE 0
+#define LVPP_LINESEARCH_BT 1
+#define LVPP_SNES_DIVERGED_LINE_SEARCH (-6)
 
 typedef struct lvpp_stats {
   int64_t num_rows;          /* global rows of the mixed system (2 * owned nodes summed over ranks) */
@@ -210,6 +217,98 @@ int lvpp_comm_unique_id(uint8_t* h_id128);
 int lvpp_comm_init(lvpp_handle h, const uint8_t* h_id128, int32_t rank, int32_t nranks);
 /* owner -> ghost update of a mixed vector (Vec.ghostUpdate(INSERT, FORWARD), problem.py:56) */
 int lvpp_halo_forward(lvpp_handle h, double* d_v);
+
+/* =====================================================================================================
+ * The other LVPP formulations of the reference behind one generic
+ * mixed-form engine: per-formulation element kernels, an atomic-free cell-to-nnz gather into a CSR
+ * matrix (the sparsity of dolfinx.fem.petsc.create_matrix: union over integration entities of
+ * dofs x dofs), fp64 CSR SpMV, dof-block-Jacobi preconditioned restarted GMRES and the SNES newtonls
+ * loop with line search none or bt.  Single GPU.
+ *
+ *   LVPP_FORM_GRADIENT    examples/06_gradient_constraints/gradient_constraint_dolfinx.py:100-107
+ *       u in P2, psi in (P1)^2 on triangles.  One integral (cells).  Local dof order: 6 u nodes, then
+ *       (psi_x, psi_y) of the 3 vertices.  params = {alpha}.  aux0 = w0 (previous iterate, :205),
+ *       coef0 = phi and coef1 = f interpolated into the primal space (:56-62), indexed by u dof.
+ *       tab_a = P2 basis [nq*6], dtab_a = its reference gradients [nq*6*2], tab_b = P1 basis [nq*3].
+ *   LVPP_FORM_MULTIPHASE  examples/04_multiphase/multiphase_dolfinx.py:64-90
+ *       u, z, psi in (P1)^4 on triangles; local dof order vertex-major, (u0..3, z0..3, psi0..3) per vertex.
+ *       params = {alpha, tau, eps0, h_scale} with epsilon = h_scale * circumradius (:52-53: 4).
+ *       aux0 = lvpp_old (:60, psi slots read), aux1 = u_prev in the u slots (:57).  tab_a = P1 basis [nq*3].
+ *   LVPP_FORM_SIGNORINI   examples/02_signorini/signorini_dolfinx.py:244-249
+ *       integral 0: tetrahedra, u in (P1)^3, local order vertex-major / component fastest;
+ *       integral 1: contact facets (triangles), 9 u dofs then the 3 psi dofs of the facet submesh.
+ *       params = {alpha, mu, lambda, gap, n_g[0], n_g[1], n_g[2]}.  aux0 = psi_k in the psi slots (:344).
+ *       integral 1: tab_a = P1 facet basis [nq*3].
+ * Vectors are plain fp64 device arrays of length num_dofs.
+ * ===================================================================================================== */
+#define LVPP_FORM_GRADIENT 1
+#define LVPP_FORM_MULTIPHASE 2
+#define LVPP_FORM_SIGNORINI 3
+
+typedef struct lvpp_form_problem* lvpp_form_handle;
+
+typedef struct lvpp_integral_desc {
+  int64_t num_entities;
+  int32_t nld;               /* mixed local dofs per entity (element matrix is nld x nld) */
+  int32_t nv;                /* geometry vertices per entity */
+  const int32_t* dofs;       /* host [num_entities * nld] */
+  const int32_t* vertices;   /* host [num_entities * nv] */
+  const int64_t* to_nnz;     /* host [num_entities * nld * nld]: CSR position of every element-matrix entry */
+  int32_t nq;
+  int32_t reserved0;
+  const double* qweights;    /* host [nq] */
+  const double* tab_a;       /* see the formulation list above */
+  const double* dtab_a;
+  const double* tab_b;
+} lvpp_integral_desc;
+
+typedef struct lvpp_form_desc {
+  int32_t form;              /* LVPP_FORM_* */
+  int32_t gdim;
+  int64_t num_dofs;
+  int64_t num_vertices;
+  const double* vertex_coords;  /* host [num_vertices * gdim] */
+  const int64_t* indptr;     /* host [num_dofs + 1]  CSR pattern, columns sorted within a row */
+  const int32_t* indices;    /* host [nnz] */
+  int64_t num_bc;
+  const int64_t* bc_dofs;    /* host [num_bc] */
+  const double* bc_values;   /* host [num_bc] */
+  int32_t num_integrals;
+  int32_t num_params;
+  const lvpp_integral_desc* integrals;
+  const double* params;      /* host [num_params] */
+  const double* coef0;       /* host [num_dofs] or NULL */
+  const double* coef1;       /* host [num_dofs] or NULL */
+  int64_t num_blocks;        /* dof blocks of the Jacobi preconditioner (e.g. the dofs of one mesh node) */
+  const int64_t* block_ptr;  /* host [num_blocks + 1] */
+  const int32_t* block_dofs; /* host [block_ptr[num_blocks]], every dof in exactly one block, block size <= 16 */
+} lvpp_form_desc;
+
+int lvpp_form_create(const lvpp_form_desc* desc, lvpp_form_handle* out);
+int lvpp_form_destroy(lvpp_form_handle h);
+/* alpha.value = ... and the other constants of the form */
+int lvpp_form_set_param(lvpp_form_handle h, int32_t index, double value);
+/* previous-iterate data read by the residual (w0 / lvpp_old / u_prev / psi_k): which = 0, 1; d_v [num_dofs] */
+int lvpp_form_set_aux(lvpp_form_handle h, int32_t which, const double* d_v);
+/* Dirichlet values g (u_bc.x.array[...] = disp, signorini_dolfinx.py:322): h_values [num_bc] in bc_dofs order */
+int lvpp_form_set_bc_values(lvpp_form_handle h, const double* h_values);
+/* residual with lifting and set_bc (src/lvpp/problem.py:54-67); leaves the Jacobian at d_x assembled */
+int lvpp_form_assemble_residual(lvpp_form_handle h, const double* d_x, double* d_F, double* h_fnorm);
+/* CSR values of the last assembled Jacobian (assemble_matrix with bcs, problem.py:75-77); d_values [nnz] */
+int lvpp_form_get_jacobian_values(lvpp_form_handle h, double* d_values);
+int lvpp_form_spmv(lvpp_form_handle h, const double* d_v, double* d_y);
+int lvpp_form_linear_solve(lvpp_form_handle h, const double* d_rhs, double* d_y, const lvpp_newton_opts* opts,
+                           int32_t* its, int32_t* reason, double* h_rnorm);
+int lvpp_form_newton_solve(lvpp_form_handle h, double* d_x, const lvpp_newton_opts* opts, int32_t* its,
+                           int32_t* reason, double* h_fnorm, int32_t* linear_its);
+/* assemble_scalar of |primal(x) - primal(x0)|^2 dx (gradient_constraint_dolfinx.py:166-168,
+ * multiphase_dolfinx.py:166-169) or, for LVPP_FORM_SIGNORINI, the discrete sum over the u dofs of
+ * (x - x0)^2 (signorini_dolfinx.py:337-339) */
+int lvpp_form_increment_sq(lvpp_form_handle h, const double* d_x, const double* d_x0, double* h_out);
+int lvpp_form_get_stats(lvpp_form_handle h, lvpp_stats* out);
+/* mean device time (ms) of `reps` launches of the element kernels + gathers (assembly) and of the CSR SpMV */
+int lvpp_form_time_kernels(lvpp_form_handle h, const double* d_x, int32_t reps, double* h_ms_assembly,
+                           double* h_ms_spmv);
 
 #ifdef __cplusplus
 }

@@ -61,3 +61,131 @@ def solve_obstacle(problem, max_outer=100, alpha_scheme="constant", alpha_max=1e
             break
         xk = x.copy()
     return x, hist
+
+
+def solve_gradient_constraint(problem, max_iterations=25, alpha_scheme="doubling", alpha_0=1.0, alpha_c=1.0,
+                              stopping_tol=1e-8, verbose=False):
+    """examples/06_gradient_constraints/gradient_constraint_dolfinx.py:113-132,171-205: alpha schedule with i
+    from 0 (:172-177), SNES newtonls / line search none / atol = rtol = stol = 1e-9 / max_it 20 (:118-131), stop on
+    ||u - u0||_L2 < tol (:185,199), w0 <- sol (:205).  ``problem``: oracle.forms.GradientConstraintOracle."""
+    x = np.zeros(problem.num_rows)
+    problem.w0 = x.copy()
+    hist = {"newton_steps": [], "alpha": [], "l2_diff": [], "reason": []}
+    for i in range(max_iterations):
+        if alpha_scheme == "linear":
+            problem.alpha = alpha_0 + alpha_c * i
+        elif alpha_scheme == "doubling":
+            problem.alpha = alpha_0 * 2**i
+        else:
+            problem.alpha = alpha_0
+        xn, reason, n, _ = snes.newton_ls(problem.assemble_residual, problem.jacobian, x, "none",
+                                          rtol=1e-9, atol=1e-9, stol=1e-9, max_it=20)
+        if reason <= 0:
+            raise RuntimeError(f"SNES did not converge: reason {reason}")
+        x = xn
+        diff = np.sqrt(problem.l2_increment_sq(x, problem.w0))
+        hist["newton_steps"].append(n)
+        hist["alpha"].append(problem.alpha)
+        hist["l2_diff"].append(diff)
+        hist["reason"].append(reason)
+        if verbose:
+            print(f"iteration {i + 1}: alpha {problem.alpha} newton {n} |delta u| {diff:.3e}")
+        if diff < stopping_tol:
+            break
+        problem.w0 = x.copy()
+    return x, hist
+
+
+def multiphase_initial_condition(coords, cells, num_species=4, tol=1e-14):
+    """u_prev of multiphase_dolfinx.py:92-125: species 0 everywhere, then species 1 / 2 / 3 interpolated on
+    the cells whose vertices all lie in three rectangles (locate_entities marks an entity when the
+    marker is true at all of its vertices)."""
+    x, y = coords[:, 0], coords[:, 1]
+    rectangle = (0.2 - tol <= y) & (y <= 0.75 + tol) & (0.2 - tol <= x) & (x <= 0.8 + tol)
+    lower_left = (y <= 0.5 + tol) & (0.2 - tol <= y) & (0.2 - tol <= x) & (x <= 0.5 + tol)
+    lower_right = (y <= 0.5 + tol) & (0.2 <= y + tol) & (0.5 - tol <= x) & (x <= 0.8 + tol)
+    u = np.zeros((coords.shape[0], num_species))
+    u[:, 0] = 1.0
+    for species, marker in ((1, rectangle), (2, lower_left), (3, lower_right)):
+        inside = np.all(marker[cells], axis=1)
+        nodes = np.unique(cells[inside])
+        u[nodes, :] = 0.0
+        u[nodes, species] = 1.0
+    return u
+
+
+def solve_multiphase(problem, num_steps=1, max_iterations=20, alpha_scheme="constant", alpha_0=1.0, alpha_c=1.0,
+                     alpha_max=50.0, stopping_tol=1e-5, verbose=False):
+    """multiphase_dolfinx.py:174-233: per time step psi <- ln(|u| + 1e-7) + 1 in sol and lvpp_old (:190-196),
+    u_old <- 0; LVPP loop with i from 1 (:199-205), SNES newtonls / bt / atol = rtol = 1e-8 / max_it 25 (:128-143),
+    lvpp_old <- sol, stop on ||u - u_old||_L2 < tol (:210-225); u_prev <- u (:227).
+    ``problem``: oracle.forms.MultiphaseOracle with u_prev set."""
+    ns, N = problem.NS, problem.N
+    x = np.zeros(problem.num_rows)
+    newton_its, lvpp_its = [], []
+    for j in range(1, num_steps + 1):
+        X = x.reshape(N, 3, ns)
+        psi0 = np.log(np.abs(X[:, 0, :]) + 1e-7) + 1.0
+        X[:, 2, :] = psi0
+        problem.lvpp_old.reshape(N, 3, ns)[:, 2, :] = psi0
+        u_old = np.zeros((N, ns))
+        total = 0
+        for i in range(1, max_iterations + 1):
+            if alpha_scheme == "linear":
+                problem.alpha = min(alpha_0 + alpha_c * i, alpha_max)
+            elif alpha_scheme == "doubling":
+                problem.alpha = min(alpha_0 * 2**i, alpha_max)
+            else:
+                problem.alpha = alpha_0
+            xn, reason, n, _ = snes.newton_ls(problem.assemble_residual, problem.jacobian, x, "bt",
+                                              rtol=1e-8, atol=1e-8, max_it=25)
+            if reason <= 0:
+                raise RuntimeError(f"SNES did not converge: reason {reason}")
+            x = xn
+            total += n
+            diff = np.sqrt(problem.l2_increment_sq(x, u_old))
+            if verbose:
+                print(f"step {j} iteration {i}: alpha {problem.alpha} newton {n} |delta u| {diff:.3e}")
+            u_old = x.reshape(N, 3, ns)[:, 0, :].copy()
+            problem.lvpp_old = x.copy()
+            if diff < stopping_tol:
+                break
+        problem.u_prev = x.reshape(N, 3, ns)[:, 0, :].copy()
+        newton_its.append(total)
+        lvpp_its.append(i)
+    return x, {"newton_iterations": newton_its, "lvpp_iterations": lvpp_its}
+
+
+def solve_signorini(problem, max_iterations=25, alpha_scheme="doubling", alpha_0=1.0, alpha_c=1.0,
+                    newton_tol=1e-6, tol=1e-6, verbose=False):
+    """examples/02_signorini/signorini_dolfinx.py:317-358: it from 1; alpha (:324-329); SNES tolerances 10 tol on
+    the first step, as atol and rtol (:331-332); line search none, max_it PETSc default 50; stop on the discrete
+    ||u - u_prev||_2 <= tol (:337-342); u_prev <- u, psi_k <- psi (:343-344).
+    ``problem``: oracle.forms.SignoriniOracle."""
+    x = np.zeros(problem.num_rows)
+    nu = problem.gd * problem.N
+    u_prev = np.zeros(nu)
+    iterations = []
+    it = 0
+    for it in range(1, max_iterations + 1):
+        if alpha_scheme == "linear":
+            problem.alpha = alpha_0 + alpha_c * it
+        elif alpha_scheme == "doubling":
+            problem.alpha = alpha_0 * 2**it
+        else:
+            problem.alpha = alpha_0
+        stol = 10 * newton_tol if it < 2 else newton_tol
+        xn, reason, n, _ = snes.newton_ls(problem.assemble_residual, problem.jacobian, x, "none",
+                                          rtol=stol, atol=stol, max_it=50)
+        if reason <= 0:
+            raise RuntimeError(f"SNES did not converge: reason {reason}")  # snes_error_if_not_converged (:279)
+        x = xn
+        iterations.append(n)
+        normed_diff = np.linalg.norm(x[:nu] - u_prev)
+        if verbose:
+            print(f"it {it}: alpha {problem.alpha} newton {n} increment {normed_diff:.3e}")
+        if normed_diff <= tol:
+            break
+        u_prev = x[:nu].copy()
+        problem.psi_k = x[nu:].copy()
+    return x, {"it": it, "iterations": iterations}

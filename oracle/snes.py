@@ -70,3 +70,93 @@ def newton_ls_none(residual, jacobian, x0, rtol=1e-8, atol=1e-50, stol=1e-8, max
         if reason:
             return x, reason, its, hist
     return x, DIVERGED_MAX_IT, its, hist
+
+
+DIVERGED_LINE_SEARCH = -6
+
+
+def linesearch_bt(residual, x, F, y, fnorm, Jy, alpha=1e-4, maxstep=1e8, steptol=1e-12, max_it=40):
+    """PETSc SNESLineSearchApply_BT, cubic order -- the default line search of ``newtonls`` when
+    ``snes_linesearch_type`` is not set (examples/04_multiphase/multiphase_dolfinx.py:128-143).
+    Restated from memory of petsc/src/snes/linesearch/impls/bt/linesearchbt.c [3P-mem]: sufficient
+    decrease of 0.5 ||F||^2 along x - lambda y with slope F.(J y), quadratic then cubic backtracking.
+    Returns (x_new, F_new, gnorm, lambda, ok)."""
+    ynorm = np.linalg.norm(y)
+    if ynorm == 0.0:
+        return x.copy(), F.copy(), fnorm, 0.0, True
+    if ynorm > maxstep:
+        y = y * (maxstep / ynorm)
+        ynorm = maxstep
+    f = fnorm * fnorm
+    initslope = float(np.dot(F, Jy))
+    if initslope > 0.0:
+        initslope = -initslope
+    if initslope == 0.0:
+        initslope = -1.0
+    rellength = np.max(np.abs(y) / np.maximum(np.abs(x), 1.0))
+    minlambda = steptol / rellength
+    lam = 1.0
+    w = x - lam * y
+    G = residual(w)
+    gnorm = np.linalg.norm(G)
+    g = gnorm * gnorm
+    if not np.isfinite(gnorm):
+        return w, G, gnorm, lam, False
+    if 0.5 * g <= 0.5 * f + lam * alpha * initslope:
+        return w, G, gnorm, lam, True
+    # quadratic fit
+    lamtemp = -initslope / (g - f - 2.0 * lam * initslope)
+    lamprev, gprev = lam, g
+    if lamtemp > 0.5 * lam:
+        lamtemp = 0.5 * lam
+    lam = 0.1 * lam if lamtemp <= 0.1 * lam else lamtemp
+    for _ in range(max_it):
+        if lam <= minlambda:
+            return w, G, gnorm, lam, False
+        w = x - lam * y
+        G = residual(w)
+        gnorm = np.linalg.norm(G)
+        g = gnorm * gnorm
+        if 0.5 * g <= 0.5 * f + lam * alpha * initslope:
+            return w, G, gnorm, lam, True
+        t1 = 0.5 * (g - f) - lam * initslope
+        t2 = 0.5 * (gprev - f) - lamprev * initslope
+        a = (t1 / (lam * lam) - t2 / (lamprev * lamprev)) / (lam - lamprev)
+        b = (-lamprev * t1 / (lam * lam) + lam * t2 / (lamprev * lamprev)) / (lam - lamprev)
+        d = b * b - 3.0 * a * initslope
+        if d < 0.0:
+            d = 0.0
+        lamtemp = -initslope / (2.0 * b) if a == 0.0 else (-b + np.sqrt(d)) / (3.0 * a)
+        lamprev, gprev = lam, g
+        if lamtemp > 0.5 * lam:
+            lamtemp = 0.5 * lam
+        lam = 0.1 * lam if lamtemp <= 0.1 * lam else lamtemp
+    return w, G, gnorm, lam, False
+
+
+def newton_ls(residual, jacobian, x0, linesearch="none", rtol=1e-8, atol=1e-50, stol=1e-8, max_it=50, divtol=1e4):
+    """SNESSolve_NEWTONLS with line search "none" (basic, full step) or "bt".  Returns (x, reason, its, hist)."""
+    if linesearch in ("none", "basic"):
+        return newton_ls_none(residual, jacobian, x0, rtol=rtol, atol=atol, stol=stol, max_it=max_it, divtol=divtol)
+    x = x0.copy()
+    F = residual(x)
+    fnorm = np.linalg.norm(F)
+    fnorm0, ttol, hist = fnorm, fnorm * rtol, [fnorm]
+    reason = converged_default(0, 0.0, 0.0, fnorm, ttol, fnorm0, atol, stol, divtol)
+    if reason:
+        return x, reason, 0, hist
+    for i in range(max_it):
+        J = jacobian(x)
+        y = spla.splu(J.tocsc()).solve(F)
+        if not np.all(np.isfinite(y)):
+            return x, DIVERGED_LINEAR_SOLVE, i, hist
+        xn, Fn, gnorm, lam, ok = linesearch_bt(residual, x, F, y, fnorm, J @ y)
+        if not ok:
+            return x, DIVERGED_LINE_SEARCH, i, hist
+        snorm = np.linalg.norm(xn - x)
+        x, F, fnorm = xn, Fn, gnorm
+        hist.append(fnorm)
+        reason = converged_default(i + 1, np.linalg.norm(x), snorm, fnorm, ttol, fnorm0, atol, stol, divtol)
+        if reason:
+            return x, reason, i + 1, hist
+    return x, DIVERGED_MAX_IT, max_it, hist

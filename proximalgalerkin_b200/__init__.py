@@ -5,7 +5,7 @@ own API surface (src/lvpp/__init__.py:1-9 exports ``SNESProblem`` and ``SNESSolv
 use the ``NonlinearProblem(...).solve()`` call shape).  Host code is Python; all arithmetic runs in
 hand-written sm_100a CUDA kernels reached through the C ABI of ``include/lvpp_b200.h``.
 """
-from . import fem, mesh, obstacle_pg, quadrature
+from . import fem, forms, gradient_constraints, mesh, multiphase, obstacle_pg, quadrature, signorini
 from .problem import (
     DeviceMatrix,
     DeviceProblem,
@@ -32,4 +32,8 @@ __all__ = [
     "mesh",
     "quadrature",
     "obstacle_pg",
+    "forms",
+    "gradient_constraints",
+    "multiphase",
+    "signorini",
 ]

@@ -14,6 +14,8 @@ OK = 0
 E_INVALID, E_CUDA, E_CAPACITY, E_COMM, E_NOGPU = -1, -2, -3, -4, -5
 OBSTACLE_ARRAY, OBSTACLE_PHI_SET = 0, 1
 PC_JACOBI, PC_CHEBYSHEV, PC_MG = 0, 1, 2
+LINESEARCH_NONE, LINESEARCH_BT = 0, 1
+FORM_GRADIENT, FORM_MULTIPHASE, FORM_SIGNORINI = 1, 2, 3
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -73,11 +75,58 @@ class NewtonOpts(C.Structure):
         ("ksp_max_it", C.c_int32),
         ("pc_type", C.c_int32),
         ("pc_degree", C.c_int32),
+        ("snes_linesearch", C.c_int32),
+        ("ksp_restart", C.c_int32),
     ]
 
     @classmethod
     def defaults(cls):
-        return cls(1e-8, 1e-50, 1e-8, 1e4, 50, 1e-12, 1e-50, 100000, PC_JACOBI, 0)
+        return cls(1e-8, 1e-50, 1e-8, 1e4, 50, 1e-12, 1e-50, 100000, PC_JACOBI, 0, LINESEARCH_NONE, 0)
+
+
+class IntegralDesc(C.Structure):
+    """struct lvpp_integral_desc"""
+
+    _fields_ = [
+        ("num_entities", C.c_int64),
+        ("nld", C.c_int32),
+        ("nv", C.c_int32),
+        ("dofs", c_int32_p),
+        ("vertices", c_int32_p),
+        ("to_nnz", c_int64_p),
+        ("nq", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("qweights", c_double_p),
+        ("tab_a", c_double_p),
+        ("dtab_a", c_double_p),
+        ("tab_b", c_double_p),
+    ]
+
+
+class FormDesc(C.Structure):
+    """struct lvpp_form_desc"""
+
+    _fields_ = [
+        ("form", C.c_int32),
+        ("gdim", C.c_int32),
+        ("num_dofs", C.c_int64),
+        ("num_vertices", C.c_int64),
+        ("vertex_coords", c_double_p),
+        ("indptr", c_int64_p),
+        ("indices", c_int32_p),
+        ("num_bc", C.c_int64),
+        ("bc_dofs", c_int64_p),
+        ("bc_values", c_double_p),
+        ("num_integrals", C.c_int32),
+        ("num_params", C.c_int32),
+        ("integrals", C.POINTER(IntegralDesc)),
+        ("params", c_double_p),
+        ("coef0", c_double_p),
+        ("coef1", c_double_p),
+        ("num_blocks", C.c_int64),
+        ("block_ptr", c_int64_p),
+        ("block_dofs", c_int32_p),
+    ]
 
 
 class Stats(C.Structure):
@@ -141,6 +190,19 @@ SIGNATURES = {
     "lvpp_comm_unique_id": (C.c_int, [c_uint8_p]),
     "lvpp_comm_init": (C.c_int, [H, c_uint8_p, C.c_int32, C.c_int32]),
     "lvpp_halo_forward": (C.c_int, [H, VP]),
+    "lvpp_form_create": (C.c_int, [C.POINTER(FormDesc), C.POINTER(H)]),
+    "lvpp_form_destroy": (C.c_int, [H]),
+    "lvpp_form_set_param": (C.c_int, [H, C.c_int32, C.c_double]),
+    "lvpp_form_set_aux": (C.c_int, [H, C.c_int32, VP]),
+    "lvpp_form_set_bc_values": (C.c_int, [H, c_double_p]),
+    "lvpp_form_assemble_residual": (C.c_int, [H, VP, VP, c_double_p]),
+    "lvpp_form_get_jacobian_values": (C.c_int, [H, VP]),
+    "lvpp_form_spmv": (C.c_int, [H, VP, VP]),
+    "lvpp_form_linear_solve": (C.c_int, [H, VP, VP, C.POINTER(NewtonOpts), c_int32_p, c_int32_p, c_double_p]),
+    "lvpp_form_newton_solve": (C.c_int, [H, VP, C.POINTER(NewtonOpts), c_int32_p, c_int32_p, c_double_p, c_int32_p]),
+    "lvpp_form_increment_sq": (C.c_int, [H, VP, VP, c_double_p]),
+    "lvpp_form_get_stats": (C.c_int, [H, C.POINTER(Stats)]),
+    "lvpp_form_time_kernels": (C.c_int, [H, VP, C.c_int32, c_double_p, c_double_p]),
 }
 
 _lib = None

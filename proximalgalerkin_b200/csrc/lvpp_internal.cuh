@@ -237,6 +237,49 @@ __host__ __device__ __forceinline__ int lvpp_sym(int a, int b, int nld) {
   return a * nld - (a * (a - 1)) / 2 + (b - a);
 }
 
+// ------------------------------------------------------------------------------------------------
+// geometry of an affine simplex: |det J| and J^{-1} (rows = reference directions)
+template <int TDIM>
+__device__ __forceinline__ double cell_geometry(const double* __restrict__ coords,
+                                                const int32_t* __restrict__ nodes, double (*Jinv)[TDIM]) {
+  double x0[TDIM], J[TDIM][TDIM];  // J[d][k] = x_{k+1}[d] - x_0[d]
+#pragma unroll
+  for (int d = 0; d < TDIM; ++d) x0[d] = coords[(int64_t)nodes[0] * TDIM + d];
+#pragma unroll
+  for (int k = 0; k < TDIM; ++k)
+#pragma unroll
+    for (int d = 0; d < TDIM; ++d) J[d][k] = coords[(int64_t)nodes[k + 1] * TDIM + d] - x0[d];
+  double det;
+  if (TDIM == 2) {
+    det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    const double id = 1.0 / det;
+    Jinv[0][0] = J[1][1] * id;  Jinv[0][1] = -J[0][1] * id;
+    Jinv[1][0] = -J[1][0] * id; Jinv[1][1] = J[0][0] * id;
+  } else {
+    const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+    const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+    const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+    const double id = 1.0 / det;
+    Jinv[0][0] = c00 * id;
+    Jinv[1][0] = c01 * id;
+    Jinv[2][0] = c02 * id;
+    Jinv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+    Jinv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+    Jinv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+    Jinv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+    Jinv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+    Jinv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+  }
+  return fabs(det);
+}
+
+// stage the quadrature / basis tables in shared memory (all threads read the same entry: broadcast)
+__device__ __forceinline__ void stage_tables(double* s_tab, const double* __restrict__ tab, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s_tab[i] = tab[i];
+  __syncthreads();
+}
+
 // ---- cross-TU entry points --------------------------------------------------------------------
 int lvpp_build_pattern(lvpp_problem* h);                      // setup.cu
 int lvpp_build_constant_operators(lvpp_problem* h, const lvpp_obstacle_desc* d);  // assembly.cu

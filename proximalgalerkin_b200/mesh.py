@@ -139,9 +139,27 @@ def _structured(n, lo, hi, rank, nranks, cube_to_simplices, cell_name):
     )
 
 
-def create_rectangle(nx, ny, lo=(-1.0, -1.0), hi=(1.0, 1.0), rank=0, nranks=1):
+def create_rectangle(nx, ny, lo=(-1.0, -1.0), hi=(1.0, 1.0), rank=0, nranks=1, diagonal="right"):
     """[lo, hi] rectangle, nx x ny squares, each split by its "right" diagonal (dolfinx
-    DiagonalType.right); partitioned into slabs along y."""
+    DiagonalType.right); partitioned into slabs along y.  ``diagonal="crossed"`` (single rank) splits
+    every square into four triangles around its centre (DiagonalType.crossed,
+    examples/04_multiphase/multiphase_dolfinx.py:34-36); the centres are numbered after the grid vertices."""
+    if diagonal == "crossed":
+        if nranks != 1:
+            raise NotImplementedError("crossed meshes are single-rank")
+        xs, ys = np.linspace(lo[0], hi[0], nx + 1), np.linspace(lo[1], hi[1], ny + 1)
+        X, Y = np.meshgrid(xs, ys, indexing="xy")
+        grid = np.stack([X.ravel(), Y.ravel()], axis=1)
+        i, j = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+        v00 = (j * (nx + 1) + i).ravel()
+        v10, v01, v11 = v00 + 1, v00 + nx + 1, v00 + nx + 2
+        mid = (nx + 1) * (ny + 1) + np.arange(nx * ny)
+        centres = 0.25 * (grid[v00] + grid[v10] + grid[v01] + grid[v11])
+        cells = np.stack([np.stack([v00, v10, mid], 1), np.stack([v10, v11, mid], 1), np.stack([v11, v01, mid], 1),
+                          np.stack([v01, v00, mid], 1)], axis=1).reshape(-1, 3)
+        return from_arrays(np.vstack([grid, centres]), cells)
+    if diagonal != "right":
+        raise ValueError(diagonal)
 
     def split(base, strides, lo_off, hi_off):
         v00 = base + lo_off

@@ -334,7 +334,7 @@ class DeviceProblem:
 
 # ---------------------------------------------------------------------------------------------
 # PETSc-style options
-def newton_options(options):
+def newton_options(options, generic=False):
     """Translate a PETSc options dict (keys without prefix, obstacle_pg.py:128-139) to lvpp_newton_opts.
 
     ``ksp_type preonly`` + ``pc_type lu`` (the reference's direct solve) maps to MINRES converged to
@@ -342,9 +342,16 @@ def newton_options(options):
     iterates of an exact solve to rounding."""
     o = _capi.NewtonOpts.defaults()
     opts = dict(options or {})
-    ls = opts.get("snes_linesearch_type", "none")
-    if ls not in ("none", "basic"):
-        raise NotImplementedError(f"snes_linesearch_type {ls!r}: only the full Newton step ('none') is implemented")
+    # PETSc's default for newtonls is "bt"; the obstacle driver always sets "none" (obstacle_pg.py:136)
+    ls = opts.get("snes_linesearch_type", "bt" if generic else "none")
+    if ls in ("none", "basic"):
+        o.snes_linesearch = _capi.LINESEARCH_NONE
+    elif ls == "bt" and generic:
+        o.snes_linesearch = _capi.LINESEARCH_BT
+    else:
+        raise NotImplementedError(f"snes_linesearch_type {ls!r}")
+    if opts.get("ksp_gmres_restart") is not None:
+        o.ksp_restart = int(opts["ksp_gmres_restart"])
     st = opts.get("snes_type", "newtonls")
     if st != "newtonls":
         raise NotImplementedError(f"snes_type {st!r}")
@@ -352,7 +359,15 @@ def newton_options(options):
     if kt not in ("preonly", "minres", "gmres", "fgmres"):
         raise NotImplementedError(f"ksp_type {kt!r}: the Newton system is solved with MINRES or GMRES")
     pc = opts.get("pc_type", "lu")
-    if pc in ("mg", "gamg") or (pc == "lu" and kt in ("gmres", "fgmres")):
+    if generic:
+        # the mixed-form engine has one Krylov solver: block-Jacobi preconditioned restarted GMRES
+        if pc not in ("lu", "bjacobi", "pbjacobi", "jacobi", "none"):
+            raise NotImplementedError(f"pc_type {pc!r}")
+        o.ksp_max_it = 20000
+        # these examples push alpha to 1e5 and stop on increments of 1e-8: the stand-in for the reference's LU
+        # has to be converged to rounding for the proximal iteration counts to agree
+        o.ksp_rtol = 1e-14
+    elif pc in ("mg", "gamg") or (pc == "lu" and kt in ("gmres", "fgmres")):
         # monolithic aggregation multigrid + restarted GMRES
         o.pc_type = _capi.PC_MG
         o.ksp_max_it = 2000
