@@ -86,6 +86,11 @@ typedef struct lvpp_obstacle_desc {
   int32_t obstacle_kind;   /* LVPP_OBSTACLE_* */
   const double* phi_obs_q; /* host [num_cells * nq] when obstacle_kind == LVPP_OBSTACLE_ARRAY */
   double f;                /* constant forcing (obstacle_pg.py:74) */
+  /* LVPP_OBSTACLE_PHI_SET on stacked domains (weak scaling): when obstacle_period > 0 the last coordinate is
+   * wrapped, x_last <- fmod(x_last - obstacle_origin, period) - period / 2, before r is taken, so every period
+   * holds its own copy of the reference's obstacle; 0 = the reference's single obstacle at the origin. */
+  double obstacle_period;
+  double obstacle_origin;
   /* halo description (all zero / NULL on one GPU): neighbour ranks and the local node lists
    * exchanged with each; send lists hold owned nodes, recv lists hold ghost nodes. */
   int32_t num_neighbors;

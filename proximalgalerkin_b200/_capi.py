@@ -52,6 +52,8 @@ class ObstacleDesc(C.Structure):
         ("obstacle_kind", C.c_int32),
         ("phi_obs_q", c_double_p),
         ("f", C.c_double),
+        ("obstacle_period", C.c_double),
+        ("obstacle_origin", C.c_double),
         ("num_neighbors", C.c_int32),
         ("neighbor_ranks", c_int32_p),
         ("send_ptr", c_int64_p),

@@ -20,6 +20,30 @@ __device__ __forceinline__ double phi_set(double r) {
   return r > b ? B + r * Cc : sqrt(fmax(r0 * r0 - r * r, 0.0));
 }
 
+// Row a of the symmetric element matrix (packed upper triangle `acc`, times `scale`) goes to the
+// incidence-ELL slot of (cell, a): NLD consecutive doubles, so the row gather streams them coalesced.
+template <int NLD>
+__device__ __forceinline__ void store_element_rows(const double* acc, double scale, const uint32_t* __restrict__ pos,
+                                                   double* __restrict__ De) {
+#pragma unroll
+  for (int a = 0; a < NLD; ++a) {
+    const uint32_t p = pos[a];
+    if (p == 0xffffffffu) continue;  // row of a ghost node: assembled by its owner
+    double* dst = De + (int64_t)p * NLD;
+    if (NLD % 2 == 0) {
+#pragma unroll
+      for (int b = 0; b < NLD; b += 2) {
+        const double v0 = scale * acc[a <= b ? lvpp_sym(a, b, NLD) : lvpp_sym(b, a, NLD)];
+        const double v1 = scale * acc[a <= b + 1 ? lvpp_sym(a, b + 1, NLD) : lvpp_sym(b + 1, a, NLD)];
+        *reinterpret_cast<double2*>(dst + b) = make_double2(v0, v1);
+      }
+    } else {
+#pragma unroll
+      for (int b = 0; b < NLD; ++b) dst[b] = scale * acc[a <= b ? lvpp_sym(a, b, NLD) : lvpp_sym(b, a, NLD)];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Setup cell kernel.  which = 0: stiffness K_e, 1: mass M_e into De (packed upper triangle);
 // which = 2: |det J| and the load vectors  int phi_obs phi_a  and  int phi_a  into ve[C][2][NLD].
@@ -27,8 +51,9 @@ template <int TDIM, int NLD>
 __global__ void __launch_bounds__(128)
 k_cell_setup(int which, int64_t C, int nq, const int32_t* __restrict__ cells,
              const double* __restrict__ coords, const double* __restrict__ tab,
-             int obstacle_kind, const double* __restrict__ phi_obs_q, double* __restrict__ De,
-             double* __restrict__ adetJ, double* __restrict__ ve) {
+             int obstacle_kind, double period, double origin, const double* __restrict__ phi_obs_q,
+             const uint32_t* __restrict__ pos,
+             double* __restrict__ De, double* __restrict__ adetJ, double* __restrict__ ve) {
   constexpr int NSYM = NLD * (NLD + 1) / 2;
   extern __shared__ double s_tab[];
   stage_tables(s_tab, tab, nq * (1 + NLD + NLD * TDIM + TDIM));
@@ -63,6 +88,11 @@ k_cell_setup(int which, int64_t C, int nq, const int32_t* __restrict__ cells,
             double xq = lam0 * xv[0][d];
 #pragma unroll
             for (int v = 1; v <= TDIM; ++v) xq += s_qp[q * TDIM + v - 1] * xv[v][d];
+            if (d == TDIM - 1 && period > 0.0) {  // one obstacle per period of the stacked domain
+              xq = fmod(xq - origin, period);
+              if (xq < 0.0) xq += period;
+              xq -= 0.5 * period;
+            }
             r2 += xq * xq;
           }
           po = phi_set(sqrt(r2));
@@ -119,8 +149,7 @@ k_cell_setup(int which, int64_t C, int nq, const int32_t* __restrict__ cells,
           for (int b = a; b < NLD; ++b, ++s) acc[s] += w * s_phi[q * NLD + a] * s_phi[q * NLD + b];
       }
     }
-#pragma unroll
-    for (int s = 0; s < NSYM; ++s) De[c * NSYM + s] = acc[s];
+    store_element_rows<NLD>(acc, 1.0, pos + c * NLD, De);
   }
 }
 
@@ -128,7 +157,8 @@ k_cell_setup(int which, int64_t C, int nq, const int32_t* __restrict__ cells,
 template <int NLD>
 __global__ void __launch_bounds__(128)
 k_cell_exp(int64_t C, int nq, const int32_t* __restrict__ cells, const double2* __restrict__ x,
-           const double* __restrict__ adetJ, const double* __restrict__ tab, double* __restrict__ De) {
+           const double* __restrict__ adetJ, const double* __restrict__ tab, const uint32_t* __restrict__ pos,
+           double* __restrict__ De) {
   constexpr int NSYM = NLD * (NLD + 1) / 2;
   extern __shared__ double s_tab[];
   stage_tables(s_tab, tab, nq * (1 + NLD));
@@ -155,21 +185,21 @@ k_cell_exp(int64_t C, int nq, const int32_t* __restrict__ cells, const double2* 
         for (int b = a; b < NLD; ++b, ++s) acc[s] += ea * s_phi[q * NLD + b];
       }
     }
-    const double adet = adetJ[c];
-#pragma unroll
-    for (int s = 0; s < NSYM; ++s) De[c * NSYM + s] = adet * acc[s];
+    store_element_rows<NLD>(acc, adetJ[c], pos + c * NLD, De);
   }
 }
 
-// Row gather (the atomic-free scatter): one thread per owned node sums the element entries of its
-// incident cells, in cell order, into per-thread shared-memory accumulators and writes its SELL
-// row.  Deterministic: the summation order is fixed by the incidence list.
+// Row gather (the atomic-free scatter): one thread per owned node sums the element rows of its
+// incident cells, in cell order, into per-thread shared-memory accumulators and writes its SELL row.
+// The element rows arrive in incidence-ELL order: at step t the 32 lanes of a warp read 32 consecutive
+// rows (NLD doubles each) and their slot-offset bytes -- fully coalesced streams.  Deterministic: the
+// summation order is fixed by the incidence list.
 template <int NLD>
-__global__ void k_row_gather(int64_t Vown, const int64_t* __restrict__ inc_ptr,
-                             const uint32_t* __restrict__ inc_val, const uint8_t* __restrict__ inc_k,
-                             const double* __restrict__ De, const int64_t* __restrict__ slice_ptr,
-                             const int32_t* __restrict__ rowlen, double* __restrict__ out) {
-  constexpr int NSYM = NLD * (NLD + 1) / 2;
+__global__ void k_row_gather(int64_t Vown, const int64_t* __restrict__ inc_ptr, const int64_t* __restrict__ ie_ptr,
+                             const uint8_t* __restrict__ ie_k, const double* __restrict__ De,
+                             const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ rowlen,
+                             double* __restrict__ out) {
+  constexpr int KB = (NLD + 3) & ~3;
   extern __shared__ double s_acc[];  // [maxw][blockDim]
   const int nt = blockDim.x, tid = threadIdx.x;
   for (int64_t i0 = blockIdx.x * (int64_t)nt; i0 < Vown; i0 += (int64_t)gridDim.x * nt) {
@@ -177,18 +207,30 @@ __global__ void k_row_gather(int64_t Vown, const int64_t* __restrict__ inc_ptr,
     if (i >= Vown) continue;
     const int len = rowlen[i];
     for (int k = 0; k < len; ++k) s_acc[k * nt + tid] = 0.0;
-    const int64_t e1 = inc_ptr[i + 1];
-    for (int64_t e = inc_ptr[i]; e < e1; ++e) {
-      const uint32_t v = inc_val[e];
-      const int64_t c = v / NLD;
-      const int a = (int)(v - (uint32_t)c * NLD);
-      const double* de = De + c * NSYM;
+    const int cnt = (int)(inc_ptr[i + 1] - inc_ptr[i]);
+    const int64_t ibase = ie_ptr[i >> 5] + (i & 31);
+    for (int t = 0; t < cnt; ++t) {
+      const int64_t slot = ibase + (int64_t)t * LVPP_SLICE;
+      const double* de = De + slot * NLD;
+      uint8_t kk[KB];
 #pragma unroll
-      for (int b = 0; b < NLD; ++b) {
-        const int k = inc_k[e * NLD + b];
-        const int s = a <= b ? lvpp_sym(a, b, NLD) : lvpp_sym(b, a, NLD);
-        s_acc[k * nt + tid] += de[s];
+      for (int q = 0; q < KB / 4; ++q) {
+        const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(ie_k + slot * KB) + q);
+        kk[4 * q] = u.x; kk[4 * q + 1] = u.y; kk[4 * q + 2] = u.z; kk[4 * q + 3] = u.w;
       }
+      double v[NLD];
+      if (NLD % 2 == 0) {
+#pragma unroll
+        for (int b = 0; b < NLD; b += 2) {
+          const double2 d2 = __ldcs(reinterpret_cast<const double2*>(de + b));
+          v[b] = d2.x; v[b + 1] = d2.y;
+        }
+      } else {
+#pragma unroll
+        for (int b = 0; b < NLD; ++b) v[b] = __ldcs(de + b);
+      }
+#pragma unroll
+      for (int b = 0; b < NLD; ++b) s_acc[kk[b] * nt + tid] += v[b];
     }
     const int64_t base = slice_ptr[i >> 5] + (i & 31);
     for (int k = 0; k < len; ++k) out[base + (int64_t)k * LVPP_SLICE] = s_acc[k * nt + tid];
@@ -358,8 +400,8 @@ static int launch_row_gather(lvpp_problem* h, double* out) {
     CK(cudaFuncSetAttribute(k_row_gather<NLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set[slot] = true;
   }
-  LAUNCH(h, k_row_gather<NLD>, lvpp_grid(h->Vown, block, 16), block, smem, h->Vown, h->inc_ptr, h->inc_val,
-         h->inc_k, h->De, h->slice_ptr, h->rowlen, out);
+  LAUNCH(h, k_row_gather<NLD>, lvpp_grid(h->Vown, block, 16), block, smem, h->Vown, h->inc_ptr, h->ie_ptr,
+         h->ie_k, h->De, h->slice_ptr, h->rowlen, out);
   CK(cudaGetLastError());
   return 0;
 }
@@ -388,7 +430,7 @@ int lvpp_build_constant_operators(lvpp_problem* h, const lvpp_obstacle_desc* d) 
   for (int which = 0; which < 3; ++which) {                                                            \
     auto kern = k_cell_setup<TD, NL>;                                                                   \
     LAUNCH(h, kern, grid, 128, smem, which, h->C, nq, h->cells, h->coords, h->tab,                      \
-           d->obstacle_kind, phi_q, h->De, h->adetJ, ve);                                               \
+           d->obstacle_kind, d->obstacle_period, d->obstacle_origin, phi_q, h->pos, h->De, h->adetJ, ve);                                               \
     CK(cudaGetLastError());                                                                             \
     if (which == 0) CKR(row_gather(h, h->K));                                                           \
     if (which == 1) CKR(row_gather(h, h->M));                                                           \
@@ -417,10 +459,10 @@ static int assemble_D(lvpp_problem* h, const double* d_x) {
   const size_t smem = sizeof(double) * h->nq * (1 + h->nld);
   const int grid = lvpp_grid(h->C, 128, 16);
   switch (h->nld) {
-    case 3: LAUNCH(h, k_cell_exp<3>, grid, 128, smem, h->C, h->nq, h->cells, (const double2*)d_x, h->adetJ, h->tab, h->De); break;
-    case 4: LAUNCH(h, k_cell_exp<4>, grid, 128, smem, h->C, h->nq, h->cells, (const double2*)d_x, h->adetJ, h->tab, h->De); break;
-    case 6: LAUNCH(h, k_cell_exp<6>, grid, 128, smem, h->C, h->nq, h->cells, (const double2*)d_x, h->adetJ, h->tab, h->De); break;
-    case 10: LAUNCH(h, k_cell_exp<10>, grid, 128, smem, h->C, h->nq, h->cells, (const double2*)d_x, h->adetJ, h->tab, h->De); break;
+    case 3: LAUNCH(h, k_cell_exp<3>, grid, 128, smem, h->C, h->nq, h->cells, (const double2*)d_x, h->adetJ, h->tab, h->pos, h->De); break;
+    case 4: LAUNCH(h, k_cell_exp<4>, grid, 128, smem, h->C, h->nq, h->cells, (const double2*)d_x, h->adetJ, h->tab, h->pos, h->De); break;
+    case 6: LAUNCH(h, k_cell_exp<6>, grid, 128, smem, h->C, h->nq, h->cells, (const double2*)d_x, h->adetJ, h->tab, h->pos, h->De); break;
+    case 10: LAUNCH(h, k_cell_exp<10>, grid, 128, smem, h->C, h->nq, h->cells, (const double2*)d_x, h->adetJ, h->tab, h->pos, h->De); break;
     default: return LVPP_E_INVALID;
   }
   CK(cudaGetLastError());
@@ -609,10 +651,10 @@ extern "C" int lvpp_time_assembly(lvpp_handle h, const double* d_x, double* d_F,
     float ms = 0.f;
     CK(cudaEventRecord(h->ev0, h->stream));
     switch (h->nld) {
-      case 3: LAUNCH(h, k_cell_exp<3>, gridc, 128, smem, h->C, h->nq, h->cells, (const double2*)d_x, h->adetJ, h->tab, h->De); break;
-      case 4: LAUNCH(h, k_cell_exp<4>, gridc, 128, smem, h->C, h->nq, h->cells, (const double2*)d_x, h->adetJ, h->tab, h->De); break;
-      case 6: LAUNCH(h, k_cell_exp<6>, gridc, 128, smem, h->C, h->nq, h->cells, (const double2*)d_x, h->adetJ, h->tab, h->De); break;
-      case 10: LAUNCH(h, k_cell_exp<10>, gridc, 128, smem, h->C, h->nq, h->cells, (const double2*)d_x, h->adetJ, h->tab, h->De); break;
+      case 3: LAUNCH(h, k_cell_exp<3>, gridc, 128, smem, h->C, h->nq, h->cells, (const double2*)d_x, h->adetJ, h->tab, h->pos, h->De); break;
+      case 4: LAUNCH(h, k_cell_exp<4>, gridc, 128, smem, h->C, h->nq, h->cells, (const double2*)d_x, h->adetJ, h->tab, h->pos, h->De); break;
+      case 6: LAUNCH(h, k_cell_exp<6>, gridc, 128, smem, h->C, h->nq, h->cells, (const double2*)d_x, h->adetJ, h->tab, h->pos, h->De); break;
+      case 10: LAUNCH(h, k_cell_exp<10>, gridc, 128, smem, h->C, h->nq, h->cells, (const double2*)d_x, h->adetJ, h->tab, h->pos, h->De); break;
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, h->stream));

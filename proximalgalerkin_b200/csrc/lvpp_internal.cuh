@@ -116,7 +116,12 @@ struct lvpp_problem {
   // incidence lists of the owned nodes (row gather map)
   int64_t* inc_ptr = nullptr;  // [Vown + 1]
   uint32_t* inc_val = nullptr; // [C * nld] cell * nld + local index, grouped by node, cell-sorted
-  uint8_t* inc_k = nullptr;    // [C * nld * nld] slot offset within the row for every local column
+  // incidence-ELL: entry t of owned node i lives at ie_ptr[i / 32] + 32 t + i % 32, so that a warp of the
+  // row gather reads 32 consecutive element rows per step (setup.cu, assembly.cu:k_row_gather)
+  int64_t* ie_ptr = nullptr;   // [nslices + 1]
+  int64_t ie_slots = 0;
+  uint32_t* pos = nullptr;     // [C * nld] incidence-ELL slot of (cell, local node); ~0u for ghost nodes
+  uint8_t* ie_k = nullptr;     // [ie_slots * kb] SELL slot offset of every local column, kb = nld rounded up to 4
   // scalar pattern in sliced ELL
   int64_t nslices = 0, sell_slots = 0, scalar_nnz = 0;
   int32_t maxw = 0;
@@ -126,7 +131,7 @@ struct lvpp_problem {
   uint32_t* col = nullptr;      // [sell_slots] column node | LVPP_COL_BC
   uint8_t* diag_k = nullptr;    // [Vown]
   double *K = nullptr, *M = nullptr, *D = nullptr;  // [sell_slots]
-  double* De = nullptr;         // [C * nsym] element scratch (cell-major)
+  double* De = nullptr;         // [ie_slots * nld] element-matrix rows in incidence-ELL order (scratch)
   // node data
   uint8_t* bc_flag = nullptr;   // [V]
   double* bc_val = nullptr;     // [V]

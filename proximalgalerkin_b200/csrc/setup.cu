@@ -71,8 +71,9 @@ __global__ void k_row_pattern(int pass, int64_t Vown, const int64_t* __restrict_
                               const uint32_t* __restrict__ inc_val,
                               const int32_t* __restrict__ cells, int32_t* __restrict__ rowlen,
                               const int64_t* __restrict__ slice_ptr, uint32_t* __restrict__ col,
-                              uint8_t* __restrict__ diag_k, uint8_t* __restrict__ inc_k,
-                              int* __restrict__ err) {
+                              uint8_t* __restrict__ diag_k, const int64_t* __restrict__ ie_ptr,
+                              uint32_t* __restrict__ pos, uint8_t* __restrict__ ie_k, int* __restrict__ err) {
+  constexpr int KB = (NLD + 3) & ~3;
   int32_t buf[LVPP_MAX_ROW + 1];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vown;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -112,8 +113,11 @@ __global__ void k_row_pattern(int pass, int64_t Vown, const int64_t* __restrict_
     for (int k = 0; k < w; ++k) col[base + (int64_t)k * LVPP_SLICE] = (uint32_t)(k < len ? buf[k] : (int32_t)i);
     for (int k = 0; k < len; ++k)
       if (buf[k] == (int32_t)i) diag_k[i] = (uint8_t)k;
+    const int64_t ibase = ie_ptr[s] + lane;
     for (int64_t e = e0; e < e1; ++e) {
       const int64_t c = inc_val[e] / NLD;
+      const int64_t slot = ibase + (e - e0) * LVPP_SLICE;
+      pos[inc_val[e]] = (uint32_t)slot;
       for (int b = 0; b < NLD; ++b) {
         const int32_t j = cells[c * NLD + b];
         int lo = 0, hi = len;
@@ -121,7 +125,7 @@ __global__ void k_row_pattern(int pass, int64_t Vown, const int64_t* __restrict_
           int mid = (lo + hi) >> 1;
           if (buf[mid] < j) lo = mid + 1; else hi = mid;
         }
-        inc_k[e * NLD + b] = (uint8_t)lo;
+        ie_k[slot * KB + b] = (uint8_t)lo;
       }
     }
   }
@@ -138,6 +142,20 @@ __global__ void k_slice_width(int64_t nslices, int64_t Vown, const int32_t* __re
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
     if (lane == 0) slice_slots[s] = (int64_t)w * LVPP_SLICE;
+  }
+}
+
+// incidence-ELL slice widths: 32 * max number of incident cells in the slice
+__global__ void k_ie_width(int64_t nslices, int64_t Vown, const int64_t* __restrict__ inc_ptr,
+                           int64_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t s = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; s < nslices;
+       s += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const int64_t i = s * LVPP_SLICE + lane;
+    int w = i < Vown ? (int)(inc_ptr[i + 1] - inc_ptr[i]) : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
+    if (lane == 0) out[s] = (int64_t)w * LVPP_SLICE;
   }
 }
 
@@ -192,7 +210,7 @@ __global__ void k_export_pattern(int64_t Vown, const int64_t* __restrict__ rowpt
 template <int NLD>
 static int row_pattern_pass(lvpp_problem* h, int pass, int* d_err) {
   LAUNCH(h, k_row_pattern<NLD>, lvpp_grid(h->Vown, 128, 16), 128, 0, pass, h->Vown, h->inc_ptr,
-         h->inc_val, h->cells, h->rowlen, h->slice_ptr, h->col, h->diag_k, h->inc_k, d_err);
+         h->inc_val, h->cells, h->rowlen, h->slice_ptr, h->col, h->diag_k, h->ie_ptr, h->pos, h->ie_k, d_err);
   CK(cudaGetLastError());
   return 0;
 }
@@ -288,7 +306,30 @@ int lvpp_build_pattern(lvpp_problem* h) {
   // 4. columns, diagonal offsets, gather map
   CKR(lvpp_dalloc(h, &h->col, (size_t)h->sell_slots));
   CKR(lvpp_dalloc(h, &h->diag_k, (size_t)h->Vown));
-  CKR(lvpp_dalloc(h, &h->inc_k, (size_t)n * h->nld, false));
+  {  // incidence-ELL slice pointers, then the (cell, local node) -> slot map and the slot-offset bytes
+    int64_t* iw = nullptr;
+    CKR(lvpp_dalloc(h, &iw, (size_t)h->nslices + 1));
+    CKR(lvpp_dalloc(h, &h->ie_ptr, (size_t)h->nslices + 1));
+    LAUNCH(h, k_ie_width, lvpp_grid(h->nslices * 32, 256, 16), 256, 0, h->nslices, h->Vown, h->inc_ptr, iw);
+    CK(cudaGetLastError());
+    size_t sb = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, sb, iw, h->ie_ptr, h->nslices + 1, h->stream));
+    void* st = nullptr;
+    CKR(lvpp_dalloc(h, (char**)&st, sb, false));
+    CK(cub::DeviceScan::ExclusiveSum(st, sb, iw, h->ie_ptr, h->nslices + 1, h->stream));
+    CK(cudaMemcpyAsync(&h->ie_slots, h->ie_ptr + h->nslices, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CKR(lvpp_dfree(h, st));
+    CKR(lvpp_dfree(h, iw));
+    if (h->ie_slots >= (int64_t)0xffffffffLL) {
+      lvpp_set_error("incidence-ELL has %lld slots, more than the 32-bit map holds", (long long)h->ie_slots);
+      return LVPP_E_CAPACITY;
+    }
+    const int kb = (h->nld + 3) & ~3;
+    CKR(lvpp_dalloc(h, &h->pos, (size_t)n, false));
+    CK(cudaMemsetAsync(h->pos, 0xff, sizeof(uint32_t) * n, h->stream));  // ghost nodes: no slot
+    CKR(lvpp_dalloc(h, &h->ie_k, (size_t)h->ie_slots * kb));
+  }
   CKR(row_pattern_dispatch(h, 1, d_err));
   // 5. Dirichlet flag on column indices
   LAUNCH(h, k_flag_cols, lvpp_grid(h->sell_slots, 256, 16), 256, 0, h->sell_slots, h->bc_flag, h->col);
@@ -431,7 +472,7 @@ extern "C" int lvpp_create(const lvpp_obstacle_desc* d, lvpp_handle* out) {
     CKR(lvpp_dalloc(h, &h->K, (size_t)h->sell_slots));
     CKR(lvpp_dalloc(h, &h->M, (size_t)h->sell_slots));
     CKR(lvpp_dalloc(h, &h->D, (size_t)h->sell_slots));
-    CKR(lvpp_dalloc(h, &h->De, (size_t)h->C * h->nsym, false));
+    CKR(lvpp_dalloc(h, &h->De, (size_t)h->ie_slots * h->nld, false));
     CKR(lvpp_dalloc(h, &h->adetJ, (size_t)h->C, false));
     CKR(lvpp_dalloc(h, &h->bobs, (size_t)h->Vown));
     CKR(lvpp_dalloc(h, &h->fvec, (size_t)h->Vown));

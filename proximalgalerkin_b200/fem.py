@@ -181,6 +181,7 @@ class QuadratureFunction:
         self.name = name
         self.values = None  # [num_cells, nq]
         self.builtin = None
+        self.period, self.origin = None, 0.0
 
     def interpolate(self, expr):
         V = self.function_space
@@ -191,11 +192,14 @@ class QuadratureFunction:
         self.values = np.ascontiguousarray(vals.reshape(mesh.num_cells, V.qpoints.shape[0]))
         self.builtin = None
 
-    def interpolate_phi_set(self):
+    def interpolate_phi_set(self, period=None, origin=0.0):
         """Use the closed-form obstacle of obstacle_pg.py:92-104, evaluated on the device (no
-        cells x nq host array; needed at the 20 M-row configuration)."""
+        cells x nq host array; needed at the 20 M-row configuration).  ``period``: tile the obstacle
+        along the last axis (one copy per period starting at ``origin``) -- the weak-scaling workload
+        stacks one [-1, 1]^3 problem per GPU."""
         self.values = None
         self.builtin = "phi_set"
+        self.period, self.origin = period, float(origin)
 
 
 def phi_set(x):

@@ -40,7 +40,8 @@ PETSC_OPTIONS = {  # obstacle_pg.py:128-139
 }
 
 
-def setup(msh, polynomial_order=1, quadrature_degree=6, obstacle="phi_set", f_value=0.0, petsc_options=None):
+def setup(msh, polynomial_order=1, quadrature_degree=6, obstacle="phi_set", f_value=0.0, petsc_options=None,
+          obstacle_period=None, obstacle_origin=0.0):
     """Everything obstacle_pg.py builds before the outer loop.  Returns a dict of the objects."""
     V = fem.functionspace(msh, ("Lagrange", polynomial_order), quadrature_degree=quadrature_degree)
     alpha = fem.Constant(msh, 1.0)
@@ -51,7 +52,7 @@ def setup(msh, polynomial_order=1, quadrature_degree=6, obstacle="phi_set", f_va
     sol_k = fem.Function(V)
     phi = fem.QuadratureFunction(V, name="phi")
     if obstacle == "phi_set":
-        phi.interpolate_phi_set()  # closed form evaluated on the device
+        phi.interpolate_phi_set(obstacle_period, obstacle_origin)  # closed form evaluated on the device
     elif callable(obstacle):
         phi.interpolate(obstacle)
     else:
@@ -109,8 +110,10 @@ class LvppStepper:
     time.  ``step()`` returns True while the LVPP iteration is still running."""
 
     def __init__(self, msh, polynomial_order=1, alpha_scheme="double_exponential", alpha_max=1e2, tol_exit=1e-4,
-                 max_outer=500, obstacle="phi_set", petsc_options=None, setup_objects=None):
-        s = setup_objects or setup(msh, polynomial_order, obstacle=obstacle, petsc_options=petsc_options)
+                 max_outer=500, obstacle="phi_set", petsc_options=None, setup_objects=None, obstacle_period=None,
+                 obstacle_origin=0.0):
+        s = setup_objects or setup(msh, polynomial_order, obstacle=obstacle, petsc_options=petsc_options,
+                                   obstacle_period=obstacle_period, obstacle_origin=obstacle_origin)
         self.s = s
         self.msh = msh
         self.dev = s["problem"].device_problem

@@ -162,6 +162,7 @@ class DeviceProblem:
         phi = F.phi
         if phi.builtin == "phi_set":
             d.obstacle_kind = _capi.OBSTACLE_PHI_SET
+            d.obstacle_period, d.obstacle_origin = phi.period or 0.0, phi.origin
         elif phi.values is not None:
             d.obstacle_kind = _capi.OBSTACLE_ARRAY
             d.phi_obs_q = _capi.as_ptr(arr(phi.values, np.float64), C.c_double)

@@ -221,3 +221,40 @@ def test_error_codes(lib):
     assert lib.lvpp_create(C.byref(d), C.byref(h)) == _capi.E_INVALID
     assert b"unsupported element" in lib.lvpp_last_error()
     assert lib.lvpp_set_alpha(None, 1.0) == _capi.E_INVALID
+
+
+def test_periodic_obstacle_matches_oracle(lib):
+    """The weak-scaling workload tiles the reference's obstacle along the last axis (one copy per GPU slab);
+    the device closed form with ``obstacle_period`` must equal the oracle fed with the wrapped function."""
+    import proximalgalerkin_b200 as lvpp
+    from oracle import mesh as omesh
+    from oracle import obstacle as oobs
+
+    n, slabs = 4, 3
+    lo, hi = (-1.0, -1.0, -float(slabs)), (1.0, 1.0, float(slabs))
+    msh = lvpp.mesh.create_box(n, n, n * slabs, lo=lo, hi=hi)
+    s = lvpp.obstacle_pg.setup(msh, 1, obstacle="phi_set", obstacle_period=2.0, obstacle_origin=-float(slabs))
+    dev = s["problem"].device_problem
+
+    def wrapped(x):
+        x = np.array(x, dtype=np.float64)
+        x[2] = np.mod(x[2] + slabs, 2.0) - 1.0
+        return oobs.phi_set(x)
+
+    orc = oobs.ObstacleOracle(omesh.box_kuhn(n, n, n * slabs, lo=lo, hi=hi), phi=wrapped)
+    rng = np.random.default_rng(8)
+    x, xk = 0.4 * rng.standard_normal(orc.num_rows), 0.4 * rng.standard_normal(orc.num_rows)
+    dev.set_alpha(1.9)
+    dev.set_previous(xk)
+    X, F = lvpp.DeviceVector(dev.n, dev.device), lvpp.DeviceVector(dev.n, dev.device)
+    X.set(x)
+    dev.assemble_residual(X, F)
+    assert _rel(F.numpy(), orc.assemble_residual(x, xk, 1.9)) < TOL_ASSEMBLY
+    # every slab sees the same obstacle: the load vector is periodic, unlike with a single obstacle
+    s1 = lvpp.obstacle_pg.setup(msh, 1, obstacle="phi_set")
+    d1 = s1["problem"].device_problem
+    d1.set_alpha(1.9)
+    d1.set_previous(xk)
+    F1 = lvpp.DeviceVector(d1.n, d1.device)
+    d1.assemble_residual(X, F1)
+    assert _rel(F1.numpy(), F.numpy()) > 1e-3
