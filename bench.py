@@ -327,6 +327,71 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+def run_forms(args):
+    """Secondary measurement (not the driver's line): the mixed-form engine on one GPU -- element kernels +
+    gathers (assembly), CSR SpMV and the first Newton solves of the example at a moderate size."""
+    import numpy as np
+    import torch
+
+    import proximalgalerkin_b200 as lvpp
+
+    torch.cuda.set_device(0)
+    name, n = args.workload, args.n
+    t0 = time.perf_counter()
+    opts = {"ksp_gmres_restart": 100, "ksp_rtol": 1e-10, "snes_error_if_not_converged": False, "snes_max_it": 2,
+            "ksp_max_it": 40000, "ksp_error_if_not_converged": False}
+    if name == "gradient":
+        s = lvpp.gradient_constraints.setup(n, n, petsc_options=opts)
+        desc = f"examples/06 gradient constraint, unit square {n}x{n}, u in P2, psi in (P1)^2, quadrature degree 10"
+    elif name == "multiphase":
+        s = lvpp.multiphase.setup(n, n, petsc_options=opts)
+        up = lvpp.multiphase.initial_condition(s["mesh"].coords, s["mesh"].cells)
+        a1 = np.zeros_like(s["sol"])
+        a1.reshape(-1, 3, 4)[:, 0, :] = up
+        s["dev"].set_aux(1, a1)
+        psi0 = np.log(1e-7) + 1.0
+        s["sol"].reshape(-1, 3, 4)[:, 2, :] = psi0
+        lo = np.zeros_like(s["sol"])
+        lo.reshape(-1, 3, 4)[:, 2, :] = psi0
+        s["dev"].set_aux(0, lo)
+        desc = f"examples/04 multiphase, crossed unit square {n}x{n}, (u, z, psi) in (P1)^4 each"
+    else:
+        msh = lvpp.mesh.create_box(n, n, n, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0))
+        s = lvpp.signorini.setup(msh, disp=-0.1, alpha_0=0.01, petsc_options=opts)
+        desc = f"examples/02 Signorini, unit cube {n}^3 x 6 tets, u in (P1)^3, psi in P1 on the contact facets"
+    setup_s = time.perf_counter() - t0
+    dev, problem = s["dev"], s["problem"]
+    X = dev.vector(s["sol"])
+    F = dev.vector()
+    dev.assemble_residual(X, F)
+    ms_asm, ms_spmv = dev.time_kernels(X, reps=10)
+    st0 = dev.stats()
+    t1 = time.perf_counter()
+    problem.solve()
+    torch.cuda.synchronize()
+    solve_s = time.perf_counter() - t1
+    st1 = dev.stats()
+    newton = st1["newton_steps"] - st0["newton_steps"]
+    kry = st1["krylov_iterations"] - st0["krylov_iterations"]
+    peak, peak_src = measured_peak()
+    nnz, rows = st1["nnz"], st1["num_rows"]
+    spmv_bytes = 12 * nnz + 16 * rows + 8 * (rows + 1)  # SURVEY 8d: values + columns, x and y, row pointer
+    line = {
+        "metric": METRIC, "value": rows * newton / solve_s if newton else None, "unit": UNIT, "n_gpus": 1, "steps": newton,
+        "dtype": "f64", "data": "synthetic", "higher_is_better": True,
+        "config": {"workload": desc, "rows": rows, "nnz": nnz, "solver": "GMRES(100) + dof-block Jacobi, ksp_rtol 1e-10, 2 Newton steps",
+                   "l2": "inputs fit L2: kernel-level numbers are L2-warm" if spmv_bytes < 120e6 else "operator exceeds L2"},
+        "krylov_iterations": kry, "ms_per_step": 1e3 * solve_s / max(newton, 1), "setup_s": setup_s,
+        "kernels": {"assembly_ms": ms_asm, "spmv_ms": ms_spmv},
+        "roofline": {"bound": "hbm", "kernel": "k_csr_spmv (fp64 CSR)", "achieved": spmv_bytes / (ms_spmv * 1e-3) / 1e9, "peak": peak,
+                     "unit": "GB/s", "frac": spmv_bytes / (ms_spmv * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": spmv_bytes},
+        "gpu_launches": st1["kernel_launches"] - st0["kernel_launches"], "device_bytes": st1["device_bytes"],
+    }
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -338,6 +403,8 @@ def main():
     ap.add_argument("--ksp-rtol", dest="ksp_rtol", type=float, default=1e-12)
     ap.add_argument("--pc", default="mg", choices=["jacobi", "mg"],
                     help="jacobi: block-diagonal MINRES; mg: multigrid-preconditioned GMRES")
+    ap.add_argument("--workload", default="obstacle", choices=["obstacle", "gradient", "multiphase", "signorini"],
+                    help="obstacle (the driver's line, configs[1]) or one of the mixed-form examples (1 GPU, --size = N)")
     ap.add_argument("--skip-e2e", dest="no_e2e", action="store_true")
     ap.add_argument("--skip-cpu", dest="no_cpu", action="store_true")
     ap.add_argument("--skip-aux", dest="no_aux", action="store_true")
@@ -346,6 +413,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "obstacle":
+        run_forms(args)
     else:
         run_b200(args)
 

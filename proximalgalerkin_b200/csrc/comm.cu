@@ -105,10 +105,22 @@ extern "C" int lvpp_comm_init(lvpp_handle h, const uint8_t* h_id128, int32_t ran
   CK(cudaMemcpyAsync(&rows, tmp, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->global_rows = (int64_t)(rows + 0.5);
+  CKR(lvpp_halo_p2p_setup(h, h->halo));
   return LVPP_OK;
 }
 
+static void halo_release(LevelHalo& H) {
+  for (void* b : H.peer_base) cudaIpcCloseMemHandle(b);
+  H.peer_base.clear();
+  if (H.arena) cudaFree(H.arena);
+  H.arena = nullptr;
+  H.p2p = false;
+}
+
 void lvpp_comm_destroy(lvpp_problem* h) {
+  halo_release(h->halo);
+  for (MgLevel& L : h->levels) halo_release(L.halo);
+  if (h->p2p_err) { cudaFreeHost(h->p2p_err); h->p2p_err = nullptr; }
   if (h->nccl_comm && g_nccl.CommDestroy) {
     g_nccl.CommDestroy((ncclComm_t)h->nccl_comm);
     h->nccl_comm = nullptr;
@@ -122,9 +134,151 @@ int lvpp_allreduce_sum(lvpp_problem* h, double* d_buf, int n) {
   return 0;
 }
 
-int lvpp_halo_forward_level(lvpp_problem* h, const LevelHalo& H, double* d_v) {
+// ---- peer-memory halo (NVLink / NVSwitch, no NCCL call on the solve path) ---------------------------
+// pack: gather the send list and store it into the neighbour's receive buffer; the last block to finish
+// raises the neighbour's flag to `seq` (system-scope release)
+__global__ void __launch_bounds__(256) k_pack_p2p(int64_t n, const int32_t* __restrict__ nodes, const double2* __restrict__ v,
+                                                   double2* __restrict__ peer_buf, int* __restrict__ counter,
+                                                   volatile unsigned long long* peer_flag, unsigned long long seq) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
+    peer_buf[p] = v[nodes[p]];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(counter, 1);
+    if (done == (int)gridDim.x - 1) {
+      *counter = 0;
+      __threadfence_system();
+      *peer_flag = seq;
+    }
+  }
+}
+// unpack: wait until every neighbour has raised its flag to `seq` (system-scope acquire), then scatter the
+// receive buffer (read past L1: the lines were written by a peer) into the ghost entries
+__global__ void __launch_bounds__(256) k_unpack_p2p(int64_t n, const int32_t* __restrict__ nodes, const double2* __restrict__ buf,
+                                                     double2* __restrict__ v, volatile unsigned long long* flags, int nflags,
+                                                     unsigned long long seq, int* __restrict__ err) {
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < nflags; ++b) {
+      const long long t0 = clock64();
+      while (flags[b] < seq)
+        if (clock64() - t0 > (1LL << 34)) {  // ~8 s: a peer died or the call sequences diverged
+          *err = 1;
+          break;
+        }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
+    v[nodes[p]] = __ldcg(&buf[p]);
+}
+
+struct P2pHello {  // what a rank tells each neighbour about its receive arena
+  cudaIpcMemHandle_t handle;
+  int64_t seg_off;   // doubles: where this neighbour's data starts inside rbuf[parity]
+  int64_t slot;      // flag index of this neighbour
+  int64_t nrecv;     // total receive count (doubles / 2) of the arena
+  int64_t ok;
+};
+
+int lvpp_halo_p2p_setup(lvpp_problem* h, LevelHalo& H) {
+  H.p2p = false;
+  if (h->nranks <= 1) return 0;
+  const char* mode = getenv("LVPP_HALO");
+  const bool want = !(mode && strcmp(mode, "nccl") == 0);
+  const int nb = H.num_neighbors;
+  const int64_t nr = H.recv_ptr.back();
+  const size_t flag_bytes = 256, buf_bytes = sizeof(double) * 2 * (size_t)(nr > 0 ? nr : 1);
+  int ok = want ? 1 : 0;
+  if (ok && !h->p2p_err) {
+    if (cudaHostAlloc((void**)&h->p2p_err, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) ok = 0;
+    else *h->p2p_err = 0;
+  }
+  if (ok && nb * sizeof(unsigned long long) > flag_bytes) ok = 0;
+  P2pHello mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok) {
+    if (cudaMalloc(&H.arena, flag_bytes + 2 * buf_bytes) != cudaSuccess) { ok = 0; H.arena = nullptr; cudaGetLastError(); }
+    else {
+      cudaMemsetAsync(H.arena, 0, flag_bytes + 2 * buf_bytes, h->stream);
+      if (cudaIpcGetMemHandle(&mine.handle, H.arena) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+    }
+  }
+  // exchange the hello records with every neighbour (through device staging buffers: NCCL moves device memory)
+  P2pHello *d_send = nullptr, *d_recv = nullptr;
+  CKR(lvpp_dalloc(h, &d_send, (size_t)nb));
+  CKR(lvpp_dalloc(h, &d_recv, (size_t)nb));
+  std::vector<P2pHello> hs((size_t)nb), hr((size_t)nb);
+  for (int b = 0; b < nb; ++b) {
+    hs[b] = mine;
+    hs[b].seg_off = 2 * H.recv_ptr[b];
+    hs[b].slot = b;
+    hs[b].nrecv = nr > 0 ? nr : 1;
+    hs[b].ok = ok;
+  }
+  CK(cudaMemcpyAsync(d_send, hs.data(), sizeof(P2pHello) * nb, cudaMemcpyHostToDevice, h->stream));
+  NCK(g_nccl.GroupStart());
+  for (int b = 0; b < nb; ++b) {
+    NCK(g_nccl.Send(d_send + b, sizeof(P2pHello), ncclChar, H.neighbor_ranks[b], (ncclComm_t)h->nccl_comm, h->stream));
+    NCK(g_nccl.Recv(d_recv + b, sizeof(P2pHello), ncclChar, H.neighbor_ranks[b], (ncclComm_t)h->nccl_comm, h->stream));
+  }
+  NCK(g_nccl.GroupEnd());
+  CK(cudaMemcpyAsync(hr.data(), d_recv, sizeof(P2pHello) * nb, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CKR(lvpp_dfree(h, d_send));
+  CKR(lvpp_dfree(h, d_recv));
+  H.peer_flag.assign((size_t)nb, nullptr);
+  H.peer_rbuf[0].assign((size_t)nb, nullptr);
+  H.peer_rbuf[1].assign((size_t)nb, nullptr);
+  for (int b = 0; b < nb && ok; ++b) {
+    if (!hr[b].ok) { ok = 0; break; }
+    void* base = nullptr;
+    if (cudaIpcOpenMemHandle(&base, hr[b].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+    H.peer_base.push_back(base);
+    H.peer_flag[b] = (unsigned long long*)base + hr[b].slot;
+    double* r0 = (double*)((char*)base + flag_bytes);
+    H.peer_rbuf[0][b] = r0 + hr[b].seg_off;
+    H.peer_rbuf[1][b] = r0 + 2 * hr[b].nrecv + hr[b].seg_off;
+  }
+  // the decision must be the same on every rank: any failure anywhere -> everybody stays on NCCL send/recv
+  double fails = ok ? 0.0 : 1.0;
+  double* d_f = nullptr;
+  CKR(lvpp_dalloc(h, &d_f, 1));
+  CK(cudaMemcpyAsync(d_f, &fails, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CKR(lvpp_allreduce_sum(h, d_f, 1));
+  CK(cudaMemcpyAsync(&fails, d_f, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CKR(lvpp_dfree(h, d_f));
+  if (fails > 0.0 || nb == 0) return 0;
+  H.flags = (unsigned long long*)H.arena;
+  H.rbuf[0] = (double*)((char*)H.arena + flag_bytes);
+  H.rbuf[1] = H.rbuf[0] + 2 * (nr > 0 ? nr : 1);
+  CKR(lvpp_dalloc(h, &H.counters, (size_t)nb));
+  H.seq = 0;
+  H.p2p = true;
+  return 0;
+}
+
+static int halo_forward_p2p(lvpp_problem* h, LevelHalo& H, double* d_v) {
+  const unsigned long long seq = ++H.seq;
+  const int par = (int)(seq & 1);
+  for (int b = 0; b < H.num_neighbors; ++b) {
+    const int64_t s0 = H.send_ptr[b], n = H.send_ptr[b + 1] - s0;
+    LAUNCH(h, k_pack_p2p, lvpp_grid(n, 256, 2), 256, 0, n, H.send_nodes + s0, (const double2*)d_v,
+           (double2*)H.peer_rbuf[par][b], H.counters + b, H.peer_flag[b], seq);
+  }
+  const int64_t nr = H.recv_ptr.back();
+  LAUNCH(h, k_unpack_p2p, lvpp_grid(nr, 256, 2), 256, 0, nr, H.recv_nodes, (const double2*)H.rbuf[par], (double2*)d_v,
+         H.flags, H.num_neighbors, seq, h->p2p_err);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int lvpp_halo_forward_level(lvpp_problem* h, LevelHalo& H, double* d_v) {
   if (h->nranks <= 1 || H.num_neighbors == 0) return 0;
   if (!h->nccl_comm) { lvpp_set_error("communicator not initialised"); return LVPP_E_COMM; }
+  if (H.p2p) return halo_forward_p2p(h, H, d_v);
   const int64_t ns = H.send_ptr.back(), nr = H.recv_ptr.back();
   if (ns > 0) {
     LAUNCH(h, k_pack, lvpp_grid(ns, 256, 4), 256, 0, ns, H.send_nodes, (const double2*)d_v, (double2*)H.send_buf);

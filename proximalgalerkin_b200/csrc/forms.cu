@@ -285,64 +285,40 @@ __global__ void __launch_bounds__(128) k_elem_multiphase(ElemArgs a) {
                  lc = hypot(xy[0][0] - xy[1][0], xy[0][1] - xy[1][1]);
     const double eps = hscale * (la * lb * lc / (4.0 * (0.5 * adet)));
     const double e2 = eps * eps;
-    double u[3][4], z[3][4], ps[3][4], po[3][4], up[3][4];
+    // pass 1 over the quadrature points: everything that depends on psi (softmax) plus the mass matrix.
+    // Only psi is live here; the terms that are linear in (u, z, psi) are applied through M and K afterwards
+    // (same quadrature sums, reassociated) so that the accumulators fit the register file.
+    double ps[3][4];
 #pragma unroll
     for (int v = 0; v < 3; ++v)
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        u[v][m] = a.xt[dl[v * 12 + m]];
-        z[v][m] = a.xt[dl[v * 12 + 4 + m]];
-        ps[v][m] = a.xt[dl[v * 12 + 8 + m]];
-        po[v][m] = a.aux0[dl[v * 12 + 8 + m]];
-        up[v][m] = a.aux1[dl[v * 12 + m]];
-      }
-    double K[6], M[6], N[6][10], Ru[3][4], Rz[3][4], Rp[3][4];
-    {
-      int k = 0;
+      for (int m = 0; m < 4; ++m) ps[v][m] = a.xt[dl[v * 12 + 8 + m]];
+    double M[6], N[6][10], S[3][4];
 #pragma unroll
-      for (int v = 0; v < 3; ++v)
-#pragma unroll
-        for (int x = v; x < 3; ++x, ++k) { K[k] = 0.0; M[k] = 0.0; }
-    }
-#pragma unroll
-    for (int k = 0; k < 6; ++k)
+    for (int k = 0; k < 6; ++k) {
+      M[k] = 0.0;
 #pragma unroll
       for (int t = 0; t < 10; ++t) N[k][t] = 0.0;
+    }
 #pragma unroll
     for (int v = 0; v < 3; ++v)
 #pragma unroll
-      for (int m = 0; m < 4; ++m) Ru[v][m] = Rz[v][m] = Rp[v][m] = 0.0;
+      for (int m = 0; m < 4; ++m) S[v][m] = 0.0;
     for (int q = 0; q < a.nq; ++q) {
       const double w = s_w[q] * adet;
       const double l[3] = {s_p1[q * 3], s_p1[q * 3 + 1], s_p1[q * 3 + 2]};
-      double uq[4], zq[4], pq[4], poq[4], upq[4], sm[4], gu[4][2], gz[4][2];
-      double esum = 0.0;
+      double sm[4], esum = 0.0;
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        uq[m] = l[0] * u[0][m] + l[1] * u[1][m] + l[2] * u[2][m];
-        zq[m] = l[0] * z[0][m] + l[1] * z[1][m] + l[2] * z[2][m];
-        pq[m] = l[0] * ps[0][m] + l[1] * ps[1][m] + l[2] * ps[2][m];
-        poq[m] = l[0] * po[0][m] + l[1] * po[1][m] + l[2] * po[2][m];
-        upq[m] = l[0] * up[0][m] + l[1] * up[1][m] + l[2] * up[2][m];
-        sm[m] = exp(pq[m]);
+        sm[m] = exp(l[0] * ps[0][m] + l[1] * ps[1][m] + l[2] * ps[2][m]);
         esum += sm[m];
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          gu[m][g] = u[0][m] * gr[0][g] + u[1][m] * gr[1][g] + u[2][m] * gr[2][g];
-          gz[m][g] = z[0][m] * gr[0][g] + z[1][m] * gr[1][g] + z[2][m] * gr[2][g];
-        }
       }
 #pragma unroll
       for (int m = 0; m < 4; ++m) sm[m] = sm[m] / esum;
 #pragma unroll
       for (int v = 0; v < 3; ++v)
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          Rz[v][m] += w * ((alpha * zq[m] - 2.0 * alpha * uq[m] + pq[m] - poq[m] - alpha) * l[v] +
-                           alpha * e2 * (gu[m][0] * gr[v][0] + gu[m][1] * gr[v][1]));
-          Ru[v][m] += w * ((uq[m] - upq[m]) * l[v] - tau * (gz[m][0] * gr[v][0] + gz[m][1] * gr[v][1]));
-          Rp[v][m] += w * (uq[m] - sm[m] - eps0 * pq[m]) * l[v];
-        }
+        for (int m = 0; m < 4; ++m) S[v][m] += w * sm[m] * l[v];
       int k = 0;
 #pragma unroll
       for (int v = 0; v < 3; ++v)
@@ -350,7 +326,6 @@ __global__ void __launch_bounds__(128) k_elem_multiphase(ElemArgs a) {
         for (int x = v; x < 3; ++x, ++k) {
           const double mm = w * l[v] * l[x];
           M[k] += mm;
-          K[k] += w * (gr[v][0] * gr[x][0] + gr[v][1] * gr[x][1]);
           int t = 0;
 #pragma unroll
           for (int m = 0; m < 4; ++m)
@@ -358,11 +333,15 @@ __global__ void __launch_bounds__(128) k_elem_multiphase(ElemArgs a) {
             for (int nn = m; nn < 4; ++nn, ++t) N[k][t] += mm * ((m == nn ? sm[m] : 0.0) - sm[m] * sm[nn]);
         }
     }
-    double* be = a.be + c * 36;
+    double K[6];
+    {
+      const double area = 0.5 * adet;  // constant gradients: the rule integrates 1 exactly
+      int k = 0;
 #pragma unroll
-    for (int v = 0; v < 3; ++v)
+      for (int v = 0; v < 3; ++v)
 #pragma unroll
-      for (int m = 0; m < 4; ++m) { be[v * 12 + m] = Ru[v][m]; be[v * 12 + 4 + m] = Rz[v][m]; be[v * 12 + 8 + m] = Rp[v][m]; }
+        for (int x = v; x < 3; ++x, ++k) K[k] = area * (gr[v][0] * gr[x][0] + gr[v][1] * gr[x][1]);
+    }
     double* cd = a.cd + c * MP_CD;
 #pragma unroll
     for (int k = 0; k < 6; ++k) { cd[k] = M[k]; cd[6 + k] = K[k]; }
@@ -371,6 +350,35 @@ __global__ void __launch_bounds__(128) k_elem_multiphase(ElemArgs a) {
 #pragma unroll
       for (int t = 0; t < 10; ++t) cd[12 + k * 10 + t] = N[k][t];
     cd[72] = e2;
+    // pass 2: residual rows through M and K
+    double* be = a.be + c * 36;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      double u[3], z[3], dp[3], du[3], pm[3];
+#pragma unroll
+      for (int x = 0; x < 3; ++x) {
+        u[x] = a.xt[dl[x * 12 + m]];
+        z[x] = a.xt[dl[x * 12 + 4 + m]];
+        pm[x] = ps[x][m];
+        dp[x] = pm[x] - a.aux0[dl[x * 12 + 8 + m]];
+        du[x] = u[x] - a.aux1[dl[x * 12 + m]];
+      }
+#pragma unroll
+      for (int v = 0; v < 3; ++v) {
+        double rz = 0.0, ru = 0.0, rp = 0.0, msum = 0.0;
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+          const double mvx = M[sym3(v, x)], kvx = K[sym3(v, x)];
+          msum += mvx;
+          rz += mvx * (alpha * z[x] - 2.0 * alpha * u[x] + dp[x]) + alpha * e2 * kvx * u[x];
+          ru += mvx * du[x] - tau * kvx * z[x];
+          rp += mvx * (u[x] - eps0 * pm[x]);
+        }
+        be[v * 12 + m] = ru;                       // EQ2, test v
+        be[v * 12 + 4 + m] = rz - alpha * msum;    // EQ1, test y
+        be[v * 12 + 8 + m] = rp - S[v][m];         // EQ3, test w
+      }
+    }
   }
 }
 __device__ __forceinline__ double entry_multiphase(const double* cd, const double* p, int i, int j) {

@@ -69,6 +69,17 @@ struct LevelHalo {
   // host copies used by the multigrid setup: ghost node of every recv slot, its number on the owning
   // rank and the neighbour slot it comes from
   std::vector<int32_t> recv_nodes_host, ghost_owner_local, ghost_nbr;
+  // peer-memory path (comm.cu): the pack kernel stores straight into the neighbour's receive buffer over
+  // NVLink and raises a sequence flag there; the unpack kernel waits for its flags.  Double-buffered by parity.
+  bool p2p = false;
+  void* arena = nullptr;                       // own IPC-exported allocation: flags | rbuf[0] | rbuf[1]
+  unsigned long long* flags = nullptr;         // [num_neighbors] raised by the neighbours
+  double* rbuf[2] = {nullptr, nullptr};        // [2 * nrecv] each
+  std::vector<double*> peer_rbuf[2];           // per neighbour: where my data goes in its rbuf[parity]
+  std::vector<unsigned long long*> peer_flag;  // per neighbour: its flag for me
+  std::vector<void*> peer_base;                // opened IPC mappings (closed at destroy)
+  int* counters = nullptr;                     // [num_neighbors] last-block detection of the pack kernels
+  unsigned long long seq = 0;
 };
 
 // one level of the aggregation multigrid hierarchy; level 0 aliases the fine operator
@@ -80,6 +91,7 @@ struct MgLevel {
   int32_t* rowlen = nullptr;
   uint8_t* diag_k = nullptr;
   double *K = nullptr, *M = nullptr, *D = nullptr;
+  float *Kf = nullptr, *Mf = nullptr, *Df = nullptr;  // single-precision copies read by the smoother sweeps
   uint8_t* bc_flag = nullptr;    // [V] u dof of the node is inactive (Dirichlet / all-Dirichlet aggregate)
   int32_t* box = nullptr;        // [Vown * 3] integer box coordinates used by the coordinate aggregation
   // transfer to the next coarser level
@@ -160,6 +172,7 @@ struct lvpp_problem {
   // communication
   int rank = 0, nranks = 1;
   void* nccl_comm = nullptr;
+  int* p2p_err = nullptr;         // pinned, device-visible: set when a peer flag was not raised in time
   LevelHalo halo;                 // fine-level halo (lvpp_obstacle_desc)
   int64_t global_rows = 0;
   // multigrid hierarchy + GMRES workspace (built lazily by lvpp_mg_setup)
@@ -168,6 +181,7 @@ struct lvpp_problem {
   double h0 = 0.0;                // node spacing used by the coordinate aggregation
   double xmin[3] = {0, 0, 0};
   int mg_nsmooth = 2;
+  bool mg_fp32 = true;            // smoother sweeps read single-precision copies of K, M, D
   // over-correction of the piecewise-constant coarse correction and relative damping of the smoother
   // (omega_l = mg_omega * 2 / (1.15 lambda_max)); tuned on the n = 215 obstacle problem (profiles/r01_mg_scan.txt)
   double mg_omega = 1.0, mg_over = 1.8;
@@ -179,6 +193,8 @@ struct lvpp_problem {
   double* coarse_bg = nullptr;    // [coarse_n] gathered right-hand side
   double* gm_V = nullptr;         // GMRES basis [(restart + 1) * 2V]
   int gm_restart = 0;
+  // classical Gram-Schmidt is repeated when less than eta2 of ||w||^2 survives the projection (Daniel et al.)
+  double gm_eta2 = 0.01;         // (0.5 = Daniel's criterion; PETSc's default never repeats; profiles/r01_mg_scan.txt)
   double* gm_h = nullptr;         // device [restart + 2]
   double* gm_h_host = nullptr;    // pinned
   double* gm_part = nullptr;      // partial sums [(restart + 2) * npartials]
@@ -294,7 +310,8 @@ int lvpp_apply_jacobian(lvpp_problem* h, const double* d_v, double* d_y, const d
 int lvpp_reduce_partials(lvpp_problem* h, int nvals, double* d_out);  // assembly.cu
 int lvpp_allreduce_sum(lvpp_problem* h, double* d_buf, int n);       // comm.cu
 int lvpp_halo_forward_impl(lvpp_problem* h, double* d_v);            // comm.cu (fine level)
-int lvpp_halo_forward_level(lvpp_problem* h, const LevelHalo& H, double* d_v);  // comm.cu
+int lvpp_halo_forward_level(lvpp_problem* h, LevelHalo& H, double* d_v);  // comm.cu
+int lvpp_halo_p2p_setup(lvpp_problem* h, LevelHalo& H);                  // comm.cu (collective)
 // packed int32 exchange over the lists of H: d_send [nsend] in send order -> d_recv [nrecv] in recv order
 int lvpp_halo_exchange_i32(lvpp_problem* h, const LevelHalo& H, const int32_t* d_send, int32_t* d_recv);  // comm.cu
 int lvpp_minres(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_newton_opts* o,

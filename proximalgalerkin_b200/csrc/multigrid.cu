@@ -343,6 +343,11 @@ __global__ void k_coarse_apply(int n, int nloc, int row0, const double* __restri
   }
 }
 
+__global__ void k_to_float(int64_t n, const double* __restrict__ a, float* __restrict__ b) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    b[i] = (float)a[i];
+}
+
 // ------------------------------------------------------------------------------------------------
 // hierarchy construction
 static int reduce_to_host(lvpp_problem* h, double* partials, int nvals, double* dst_dev, double* dst_host);
@@ -394,12 +399,12 @@ static int level_alloc_vectors(lvpp_problem* h, MgLevel& L) {
 // Dirichlet bit) of every node on its send lists; both sides take the sorted unique aggregate numbers
 // per neighbour, so the coarse send list of the owner and the coarse recv list of the receiver agree
 // entry by entry.  Coarse ghosts are numbered after the owned coarse nodes, neighbour by neighbour.
-static int build_coarse_halo(lvpp_problem* h, MgLevel& F, MgLevel& C, int64_t Vc) {
-  const LevelHalo& FH = F.halo;
+static int build_coarse_halo(lvpp_problem* h, LevelHalo& FH, MgLevel& F, MgLevel& C, int64_t Vc) {
   LevelHalo& CH = C.halo;
   C.Vown = Vc;
   C.V = Vc;
-  if (h->nranks <= 1 || FH.num_neighbors == 0) return 0;
+  if (h->nranks <= 1) return 0;
+  if (FH.num_neighbors == 0) return lvpp_halo_p2p_setup(h, CH);  // collective: take part without neighbours
   const int64_t ns = FH.send_ptr.back(), nr = FH.recv_ptr.back();
   int32_t *d_s = nullptr, *d_r = nullptr;
   CKR(lvpp_dalloc(h, &d_s, (size_t)ns, false));
@@ -465,6 +470,7 @@ static int build_coarse_halo(lvpp_problem* h, MgLevel& F, MgLevel& C, int64_t Vc
   CKR(lvpp_dfree(h, d_s));
   CKR(lvpp_dfree(h, d_r));
   CKR(lvpp_dfree(h, d_ag));
+  CKR(lvpp_halo_p2p_setup(h, CH));
   return 0;
 }
 
@@ -517,7 +523,7 @@ static int build_next_level(lvpp_problem* h, int l, bool* stop) {
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   for (void* p : {(void*)keys, (void*)skeys, (void*)vals, (void*)svals, (void*)scan, tmp, stmp}) CKR(lvpp_dfree(h, p));
-  CKR(build_coarse_halo(h, F, C, Vc));
+  CKR(build_coarse_halo(h, l == 0 ? h->halo : F.halo, F, C, Vc));
 
   // ---- coarse pattern and the Galerkin slot map: sort every fine slot by (coarse row, coarse col)
   const int64_t S = F.slots;
@@ -614,6 +620,7 @@ int lvpp_mg_setup(lvpp_problem* h) {
   h->mg_over = env_double("LVPP_MG_OVER", h->mg_over);
   h->mg_omega = env_double("LVPP_MG_OMEGA", h->mg_omega);
   h->mg_nsmooth = (int)env_double("LVPP_MG_NSMOOTH", h->mg_nsmooth);
+  h->gm_eta2 = env_double("LVPP_GMRES_ETA2", h->gm_eta2);
   // GMRES workspace (also the scratch of the collective decisions below)
   h->gm_restart = (int)env_double("LVPP_GMRES_RESTART", 50);
   if (h->gm_restart < 2 || h->gm_restart > 200) { lvpp_set_error("bad LVPP_GMRES_RESTART"); return LVPP_E_INVALID; }
@@ -626,10 +633,10 @@ int lvpp_mg_setup(lvpp_problem* h) {
   L0.V = h->V; L0.Vown = h->Vown; L0.nslices = h->nslices; L0.slots = h->sell_slots; L0.nnz = h->scalar_nnz;
   L0.slice_ptr = h->slice_ptr; L0.col = h->col; L0.rowlen = h->rowlen; L0.diag_k = h->diag_k;
   L0.K = h->K; L0.M = h->M; L0.D = h->D; L0.bc_flag = h->bc_flag;
-  L0.halo = h->halo;
-  if (h->nranks > 1 && L0.halo.num_neighbors > 0) {
+  // level 0 uses h->halo itself (the peer-memory halo keeps a sequence counter per level)
+  if (h->nranks > 1 && h->halo.num_neighbors > 0) {
     // number of every ghost node on its owner (needed when the fine level is also the coarsest)
-    LevelHalo& H = L0.halo;
+    LevelHalo& H = h->halo;
     const int64_t nr = H.recv_ptr.back();
     int32_t* d_r = nullptr;
     CKR(lvpp_dalloc(h, &d_r, (size_t)nr, false));
@@ -656,6 +663,17 @@ int lvpp_mg_setup(lvpp_problem* h) {
     CKR(build_next_level(h, l, &stop));
     if (stop) break;
   }
+  h->mg_fp32 = env_double("LVPP_MG_FP32", 1.0) != 0.0;
+  if (h->mg_fp32)
+    for (size_t l = 0; l + 1 < h->levels.size(); ++l) {
+      MgLevel& L = h->levels[l];
+      CKR(lvpp_dalloc(h, &L.Kf, (size_t)L.slots, false));
+      CKR(lvpp_dalloc(h, &L.Mf, (size_t)L.slots, false));
+      CKR(lvpp_dalloc(h, &L.Df, (size_t)L.slots, false));
+      LAUNCH(h, k_to_float, lvpp_grid(L.slots, 256, 16), 256, 0, L.slots, L.K, L.Kf);
+      LAUNCH(h, k_to_float, lvpp_grid(L.slots, 256, 16), 256, 0, L.slots, L.M, L.Mf);
+      CK(cudaGetLastError());
+    }
   // coarsest level: global numbering of all ranks' coarse nodes, rank by rank
   const MgLevel& Lc = h->levels.back();
   std::vector<double> cnt((size_t)h->nranks, 0.0);
@@ -672,7 +690,7 @@ int lvpp_mg_setup(lvpp_problem* h) {
   {
     std::vector<int32_t> gmap((size_t)Lc.V, -1);
     for (int64_t i = 0; i < Lc.Vown; ++i) gmap[i] = (int32_t)(h->coarse_off + i);
-    const LevelHalo& H = Lc.halo;
+    const LevelHalo& H = h->levels.size() == 1 ? h->halo : Lc.halo;
     for (size_t p = 0; p < H.recv_nodes_host.size() && h->nranks > 1; ++p)
       gmap[H.recv_nodes_host[p]] = (int32_t)(off[H.neighbor_ranks[H.ghost_nbr[p]]] + H.ghost_owner_local[p]);
     for (int64_t i = 0; i < Lc.V; ++i)
@@ -687,14 +705,15 @@ int lvpp_mg_setup(lvpp_problem* h) {
   if (getenv("LVPP_MG_VERBOSE") && h->rank == 0) {
     fprintf(stderr, "[lvpp mg] %d levels:", (int)h->levels.size());
     for (const MgLevel& L : h->levels) fprintf(stderr, " %lld(+%lld)", (long long)L.Vown, (long long)(L.V - L.Vown));
-    fprintf(stderr, "; coarsest dense n = %d\n", h->coarse_n);
+    fprintf(stderr, "; coarsest dense n = %d; halo %s\n", h->coarse_n,
+            h->nranks > 1 ? (h->halo.p2p ? "peer memory" : "nccl send/recv") : "none");
   }
   h->mg_ready = true;
   return 0;
 }
 
 static int level_op_local(lvpp_problem* h, MgLevel& L, int epi, double omega, const double* v, const double* b,
-                         double* y) {
+                         double* y, bool f32 = false) {
   OpArgs p = lvpp_level_op(h, L);
   p.v = (const double2*)v;
   p.y = (double2*)y;
@@ -704,15 +723,17 @@ static int level_op_local(lvpp_problem* h, MgLevel& L, int epi, double omega, co
   p.omega = omega;
   const int grid = lvpp_grid(L.Vown, 256, 6);
   if (&L == &h->levels[0]) h->fine_op_launches++;
-  LAUNCH(h, k_block_op<0>, grid, 256, 0, p);
+  if (f32 && L.Kf) LAUNCH(h, (k_block_op<0, true>), grid, 256, 0, p);
+  else LAUNCH(h, (k_block_op<0, false>), grid, 256, 0, p);
   CK(cudaGetLastError());
   return 0;
 }
 
-// ghost update of v, then the operator
-static int level_op(lvpp_problem* h, MgLevel& L, int epi, double omega, const double* v, const double* b, double* y) {
-  if (h->nranks > 1) CKR(lvpp_halo_forward_level(h, L.halo, const_cast<double*>(v)));
-  return level_op_local(h, L, epi, omega, v, b, y);
+// ghost update of v, then the operator (smoother / cycle residual: single-precision values when enabled)
+static int level_op(lvpp_problem* h, MgLevel& L, int epi, double omega, const double* v, const double* b, double* y,
+                    bool f32 = true) {
+  if (h->nranks > 1) CKR(lvpp_halo_forward_level(h, &L == &h->levels[0] ? h->halo : L.halo, const_cast<double*>(v)));
+  return level_op_local(h, L, epi, omega, v, b, y, f32 && h->mg_fp32);
 }
 
 static int build_binv(lvpp_problem* h, MgLevel& L, double omega) {
@@ -763,6 +784,12 @@ int lvpp_mg_update(lvpp_problem* h) {
     LAUNCH(h, k_galerkin, lvpp_grid(C.nnz, 256, 16), 256, 0, C.nnz, F.gal_ptr, F.gal_src, F.gal_dst, 1, F.D, F.D, C.D, C.D);
     CK(cudaGetLastError());
   }
+  if (h->mg_fp32)
+    for (int l = 0; l + 1 < nl; ++l) {
+      MgLevel& L = h->levels[l];
+      LAUNCH(h, k_to_float, lvpp_grid(L.slots, 256, 16), 256, 0, L.slots, L.D, L.Df);
+      CK(cudaGetLastError());
+    }
   // Damping: lambda_max(Binv J) is set by the stiffness block (mesh and element, not psi), so it is estimated
   // when alpha changes (once per proximal step) with a 15 % margin for its drift over the Newton steps.
   const bool estimate = !(h->mg_alpha_est == h->alpha);
@@ -894,7 +921,7 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
     if (first) {
       CK(cudaMemcpyAsync(vec(0), d_rhs, sizeof(double) * 2 * Vown, cudaMemcpyDeviceToDevice, h->stream));
     } else {
-      CKR(level_op(h, L0, EPI_RESID, 1.0, d_y, d_rhs, vec(0)));
+      CKR(level_op(h, L0, EPI_RESID, 1.0, d_y, d_rhs, vec(0), false));
     }
     LAUNCH(h, k_multi_dot, nb, 256, 0, Vown, Vb, stride2, 0, 1, (const double2*)vec(0), nb, gpart);
     CK(cudaGetLastError());
@@ -916,7 +943,7 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
       // w = J M^-1 v_j  -> stored in v_{j+1}
       double* z = nullptr;
       CKR(lvpp_mg_vcycle(h, vec(j), &z));
-      if (h->nranks > 1) CKR(lvpp_halo_forward_level(h, L0.halo, z));
+      if (h->nranks > 1) CKR(lvpp_halo_forward_level(h, h->halo, z));
       CK(cudaEventRecord(h->evs0, h->stream));
       CKR(level_op_local(h, L0, EPI_NONE, 1.0, z, nullptr, vec(j + 1)));
       CK(cudaEventRecord(h->evs1, h->stream));
@@ -944,7 +971,7 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
           h->spmv_samples++;
         }
         // selective re-orthogonalisation (Daniel et al.): only when the projection removed most of w
-        if (beta * beta > 0.5 * (hsq + beta * beta)) break;
+        if (beta * beta > h->gm_eta2 * (hsq + beta * beta)) break;
       }
       hcol[j + 1] = beta;
       ++total;
@@ -996,6 +1023,7 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
   }
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaEventSynchronize(h->ev1));
+  if (h->p2p_err && *h->p2p_err) { lvpp_set_error("peer-memory halo: a neighbour's flag was not raised in time"); return LVPP_E_COMM; }
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->t_krylov_ms += ms;

@@ -82,6 +82,7 @@ def main():
         while st1.step():
             pass
         assert st.history["newton_steps"] == st1.history["newton_steps"], (st.history, st1.history)
+        print(f"single-GPU krylov={d1.stats()['krylov_iterations']} partitioned krylov={dev.stats()['krylov_iterations']}")
         torch.save({"x": st1.x.numpy()}, "/tmp/lvpp_multi_sol.pt")
     dist.barrier()
     sol = torch.load("/tmp/lvpp_multi_sol.pt", weights_only=False)["x"].reshape(-1, 2)
