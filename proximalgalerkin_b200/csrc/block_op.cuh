@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) k_block_op(OpArgs p) {
             out.y = rp;
           } else {
             const double* B = p.binv + 4 * i;
-            out.x = vi.x + p.omega * (B[0] * ru + B[1] * rp);
+            out.x = vi.x + (isbc ? 1.0 : p.omega) * (B[0] * ru + B[1] * rp);  // Dirichlet rows exactly
             out.y = vi.y + p.omega * (B[2] * ru + B[3] * rp);
           }
         }

@@ -16,6 +16,7 @@
 #define LVPP_MAX_ROW 255      // longest scalar row (uint8 slot offsets)
 #define LVPP_SLICE 32         // sliced-ELL slice height = warp width
 #define LVPP_NUM_SMS 148      // B200
+#define MG_MAX_SWEEPS 8
 #define LVPP_COL_BC 0x80000000u  // bit 31 of a stored column index: column node is Dirichlet (u)
 
 void lvpp_set_error(const char* fmt, ...);
@@ -106,6 +107,7 @@ struct MgLevel {
   double *b = nullptr, *x = nullptr, *t = nullptr;
   double* ev = nullptr;          // [2V] power-iteration vector (lambda_max of Binv J, kept between updates)
   double omega = 0.7;            // damping of the node-block Jacobi smoother on this level
+  double sweep_omega[MG_MAX_SWEEPS] = {0};  // damping of sweep k of a smoothing step (Chebyshev roots or omega)
   double lambda = 0.0;           // last estimate of lambda_max(Binv J)
   LevelHalo halo;
 };
@@ -185,6 +187,9 @@ struct lvpp_problem {
   // over-correction of the piecewise-constant coarse correction and relative damping of the smoother
   // (omega_l = mg_omega * 2 / (1.15 lambda_max)); tuned on the n = 215 obstacle problem (profiles/r01_mg_scan.txt)
   double mg_omega = 1.0, mg_over = 1.8;
+  double mg_margin = 1.15;        // safety factor on the power-iteration estimate of lambda_max(Binv J)
+  int mg_power_its = 10;
+  double mg_cheb = 10.0;          // > 1: Chebyshev-root damping of the sweeps over [b / mg_cheb, b]; else plain damping
   double mg_alpha_est = -1.0;     // alpha of the last smoother eigenvalue estimate
   double* coarse_lu = nullptr;    // dense inverse of the coarsest operator (all ranks' rows) [nc * nc]
   int coarse_n = 0;               // global unknowns of the coarsest level

@@ -183,13 +183,13 @@ __global__ void k_galerkin(int64_t nnzc, const int64_t* __restrict__ gal_ptr, co
 // cycle kernels
 __global__ void k_build_binv(int64_t Vown, const int64_t* __restrict__ slice_ptr, const uint8_t* __restrict__ diag_k,
                              const double* __restrict__ K, const double* __restrict__ M, const double* __restrict__ D,
-                             const uint8_t* __restrict__ bc, double alpha, double omega, double* __restrict__ binv) {
+                             const uint8_t* __restrict__ bc, double alpha, double* __restrict__ binv) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vown; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t idx = slice_ptr[i >> 5] + (i & 31) + (int64_t)diag_k[i] * LVPP_SLICE;
     const double a = alpha * K[idx], m = M[idx], d = D[idx];
     double* B = binv + 4 * i;
-    if (bc[i]) {  // identity row for u (made exact under damping), psi decoupled from the masked column
-      B[0] = 1.0 / omega; B[1] = 0.0; B[2] = 0.0; B[3] = -1.0 / d;
+    if (bc[i]) {  // identity row for u (applied undamped by the sweeps), psi decoupled from the masked column
+      B[0] = 1.0; B[1] = 0.0; B[2] = 0.0; B[3] = -1.0 / d;
     } else {
       const double idet = 1.0 / (-a * d - m * m);
       B[0] = -d * idet; B[1] = -m * idet; B[2] = -m * idet; B[3] = a * idet;
@@ -198,11 +198,12 @@ __global__ void k_build_binv(int64_t Vown, const int64_t* __restrict__ slice_ptr
 }
 
 __global__ void k_smooth_first(int64_t Vown, const double2* __restrict__ b, const double* __restrict__ binv,
-                               double omega, double2* __restrict__ x) {
+                               const uint8_t* __restrict__ bc, double omega, double2* __restrict__ x) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vown; i += (int64_t)gridDim.x * blockDim.x) {
     const double2 r = b[i];
     const double* B = binv + 4 * i;
-    x[i] = make_double2(omega * (B[0] * r.x + B[1] * r.y), omega * (B[2] * r.x + B[3] * r.y));
+    const double wu = bc[i] ? 1.0 : omega;  // Dirichlet rows are solved exactly
+    x[i] = make_double2(wu * (B[0] * r.x + B[1] * r.y), omega * (B[2] * r.x + B[3] * r.y));
   }
 }
 
@@ -620,6 +621,10 @@ int lvpp_mg_setup(lvpp_problem* h) {
   h->mg_over = env_double("LVPP_MG_OVER", h->mg_over);
   h->mg_omega = env_double("LVPP_MG_OMEGA", h->mg_omega);
   h->mg_nsmooth = (int)env_double("LVPP_MG_NSMOOTH", h->mg_nsmooth);
+  if (h->mg_nsmooth < 1 || h->mg_nsmooth > MG_MAX_SWEEPS) { lvpp_set_error("bad LVPP_MG_NSMOOTH"); return LVPP_E_INVALID; }
+  h->mg_cheb = env_double("LVPP_MG_CHEB", h->mg_cheb);
+  h->mg_margin = env_double("LVPP_MG_MARGIN", h->mg_margin);
+  h->mg_power_its = (int)env_double("LVPP_MG_POWER_ITS", h->mg_power_its);
   h->gm_eta2 = env_double("LVPP_GMRES_ETA2", h->gm_eta2);
   // GMRES workspace (also the scratch of the collective decisions below)
   h->gm_restart = (int)env_double("LVPP_GMRES_RESTART", 50);
@@ -736,9 +741,9 @@ static int level_op(lvpp_problem* h, MgLevel& L, int epi, double omega, const do
   return level_op_local(h, L, epi, omega, v, b, y, f32 && h->mg_fp32);
 }
 
-static int build_binv(lvpp_problem* h, MgLevel& L, double omega) {
+static int build_binv(lvpp_problem* h, MgLevel& L) {
   LAUNCH(h, k_build_binv, lvpp_grid(L.Vown, 256, 8), 256, 0, L.Vown, L.slice_ptr, L.diag_k, L.K, L.M, L.D,
-         L.bc_flag, h->alpha, omega, L.binv);
+         L.bc_flag, h->alpha, L.binv);
   CK(cudaGetLastError());
   return 0;
 }
@@ -747,7 +752,7 @@ static int build_binv(lvpp_problem* h, MgLevel& L, double omega) {
 // omega = -1) from a fixed start vector: the estimate depends only on the operator, never on history
 static int estimate_lambda(lvpp_problem* h, MgLevel& L) {
   const int nb = h->npartials;
-  const int nit = 10;
+  const int nit = h->mg_power_its;
   LAUNCH(h, k_ev_init, lvpp_grid(L.Vown, 256, 8), 256, 0, L.Vown, (double2*)L.ev);
   CK(cudaGetLastError());
   CK(cudaMemsetAsync(L.x, 0, sizeof(double) * 2 * L.V, h->stream));
@@ -795,17 +800,30 @@ int lvpp_mg_update(lvpp_problem* h) {
   const bool estimate = !(h->mg_alpha_est == h->alpha);
   for (int l = 0; l + 1 < nl; ++l) {
     MgLevel& L = h->levels[l];
+    CKR(build_binv(h, L));
     if (estimate) {
-      CKR(build_binv(h, L, 1.0));
       CKR(estimate_lambda(h, L));
-      L.omega = h->mg_omega * std::min(1.0, 2.0 / (1.15 * L.lambda));
+      L.omega = h->mg_omega * std::min(1.0, 2.0 / (h->mg_margin * L.lambda));
+      // sweep k of a smoothing step is damped by omega_k.  Plain damped Jacobi: omega_k = omega.  Chebyshev
+      // (mg_cheb = ratio > 1): 1 / omega_k are the roots of the degree-nsmooth Chebyshev polynomial of the
+      // interval [b / ratio, b], b = 1.15 lambda_max -- the sweeps are the same kernel at the same cost, their
+      // product is the polynomial that is smallest on the upper part of the spectrum
+      const int m = h->mg_nsmooth;
+      for (int k = 0; k < m; ++k) {
+        if (h->mg_cheb > 1.0) {
+          const double b = h->mg_margin * L.lambda, a = b / h->mg_cheb;
+          L.sweep_omega[k] = 1.0 / (0.5 * (b + a) + 0.5 * (b - a) * cos(M_PI * (2 * k + 1) / (2.0 * m)));
+        } else {
+          L.sweep_omega[k] = L.omega;
+        }
+      }
     }
-    CKR(build_binv(h, L, L.omega));
   }
   h->mg_alpha_est = h->alpha;
   if (estimate && getenv("LVPP_MG_VERBOSE") && h->rank == 0) {
     fprintf(stderr, "[lvpp mg] lambda_max / omega:");
-    for (int l = 0; l + 1 < nl; ++l) fprintf(stderr, " %.3f/%.3f", h->levels[l].lambda, h->levels[l].omega);
+    for (int l = 0; l + 1 < nl; ++l)
+      fprintf(stderr, " %.3f/%.3f,%.3f", h->levels[l].lambda, h->levels[l].sweep_omega[0], h->levels[l].sweep_omega[h->mg_nsmooth - 1]);
     fprintf(stderr, "\n");
   }
   MgLevel& Lc = h->levels.back();
@@ -843,11 +861,11 @@ int lvpp_mg_vcycle(lvpp_problem* h, const double* b_in, double** z_out) {
   for (int l = 0; l < nl - 1; ++l) {
     MgLevel& L = h->levels[l];
     cur[l] = L.x; oth[l] = L.t;
-    LAUNCH(h, k_smooth_first, lvpp_grid(L.Vown, 256, 6), 256, 0, L.Vown, (const double2*)rhs[l], L.binv, L.omega,
-           (double2*)cur[l]);
+    LAUNCH(h, k_smooth_first, lvpp_grid(L.Vown, 256, 6), 256, 0, L.Vown, (const double2*)rhs[l], L.binv, L.bc_flag,
+           L.sweep_omega[0], (double2*)cur[l]);
     CK(cudaGetLastError());
     for (int s = 1; s < nsm; ++s) {
-      CKR(level_op(h, L, EPI_JACOBI, L.omega, cur[l], rhs[l], oth[l]));
+      CKR(level_op(h, L, EPI_JACOBI, L.sweep_omega[s], cur[l], rhs[l], oth[l]));
       std::swap(cur[l], oth[l]);
     }
     CKR(level_op(h, L, EPI_RESID, L.omega, cur[l], rhs[l], oth[l]));  // residual into the spare buffer
@@ -880,7 +898,7 @@ int lvpp_mg_vcycle(lvpp_problem* h, const double* b_in, double** z_out) {
            h->mg_over, (double2*)cur[l]);
     CK(cudaGetLastError());
     for (int s = 0; s < nsm; ++s) {
-      CKR(level_op(h, L, EPI_JACOBI, L.omega, cur[l], rhs[l], oth[l]));
+      CKR(level_op(h, L, EPI_JACOBI, L.sweep_omega[s], cur[l], rhs[l], oth[l]));
       std::swap(cur[l], oth[l]);
     }
   }
