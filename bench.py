@@ -170,16 +170,25 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n = args.n
     t_setup = time.perf_counter()
-    msh = lvpp.mesh.create_box(n, n, n * world, lo=(-1.0, -1.0, -float(world)), hi=(1.0, 1.0, float(world)),
-                               rank=rank, nranks=world)
+    # Weak scaling (N > 1).  "refine" (default): the reference's problem -- one obstacle on [-1,1]^3 -- on a mesh
+    # refined so that every GPU keeps ~n^3 cubes: nx = ny = round(n N^(1/3)), nz = the multiple of N nearest to nx, cut
+    # into N z-slabs.  "stack": N copies of the n^3 problem stacked along z on [-1,1]^2 x [-N,N] with one obstacle
+    # per slab (the far slabs of a single obstacle see phi = -16 and the first Newton step from psi = 0 overshoots
+    # past PETSc's divergence tolerance).  --slabs S emulates the S-GPU "stack" problem on one GPU (diagnostic).
+    slabs = max(1, args.slabs) if world == 1 else (world if args.weak == "stack" else 1)
+    if world > 1 and args.weak == "refine":
+        nxy = int(round(n * world ** (1.0 / 3.0)))
+        nz = world * max(2, int(round(nxy / world)))
+        lo, hi = (-1.0, -1.0, -1.0), (1.0, 1.0, 1.0)
+    else:
+        nxy, nz = n, n * slabs
+        lo, hi = (-1.0, -1.0, -float(slabs)), (1.0, 1.0, float(slabs))
+    msh = lvpp.mesh.create_box(nxy, nxy, nz, lo=lo, hi=hi, rank=rank, nranks=world)
     opts = {"ksp_rtol": args.ksp_rtol, "ksp_max_it": 200000}
     if args.pc == "mg":
         opts = {"ksp_rtol": args.ksp_rtol, "ksp_type": "gmres", "pc_type": "mg"}
-    # weak scaling: one copy of the reference's obstacle per GPU slab (period 2 along z), so that every rank
-    # solves the same physics; with a single obstacle at the origin the far slabs see phi = -16 and the first
-    # Newton step from psi = 0 overshoots past PETSc's divergence tolerance at 8 slabs
     st = lvpp.obstacle_pg.LvppStepper(msh, 1, "double_exponential", 1e2, 1e-4, petsc_options=opts,
-                                      obstacle_period=2.0 if world > 1 else None, obstacle_origin=-float(world))
+                                      obstacle_period=2.0 if slabs > 1 else None, obstacle_origin=-float(slabs))
     dev = st.dev
     stats0 = dev.stats()
     t_setup = time.perf_counter() - t_setup
@@ -222,35 +231,55 @@ def run_b200(args):
     kry = s1["krylov_iterations"] - s0["krylov_iterations"]
     launches = s1["kernel_launches"] - s0["kernel_launches"]
 
-    # ---- roofline of the dominant kernel (J*v): launches sampled with CUDA events inside the timed solves
-    n_s = s1["spmv_samples"] - s0["spmv_samples"]
-    spmv_ms = (s1["spmv_sampled_ms"] - s0["spmv_sampled_ms"]) / max(n_s, 1)
+    # ---- rooflines: launches sampled with CUDA events (on the library's stream) inside the timed solves
     V_own = stats0["local_rows"] // 2
     slots = stats0["sell_slots"]
-    # compulsory bytes of one J*v launch in the stored format: per slot col(4) + K,M,D (24);
-    # per node: gathered v (16) + own v (16, L2-resident) counted once as 16, y (16), bc flag (1), slice ptr (8/32)
-    spmv_bytes = 28 * slots + (16 + 16 + 1 + 0.25) * V_own
     peak, peak_src = measured_peak()
-    achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if n_s else None
-    traffic = None
-    tf = ROOT / "profiles" / "spmv_traffic.json"
-    if tf.exists():
-        try:
-            tj = json.loads(tf.read_text())
-            if int(tj.get("n", -1)) == n:
-                traffic = tj.get("dram_bytes_per_launch")
-        except Exception:
-            pass
-    roofline = {
-        "bound": "hbm", "kernel": "k_block_op<0> (J*v, 2x2-block sliced-ELL)", "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms, "launches_sampled": n_s,
+
+    def traffic_of(fname):
+        tf = ROOT / "profiles" / fname
+        if tf.exists():
+            try:
+                tj = json.loads(tf.read_text())
+                if int(tj.get("n", -1)) == n:
+                    return tj.get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        return None
+
+    # (1) fp64 J*v (k_block_op<0>): compulsory bytes in the stored format: per slot col(4) + K,M,D (24);
+    # per node: gathered v (16; the own entry is one of them), y (16), bc flag (1), slice ptr (8/32)
+    n_s = s1["spmv_samples"] - s0["spmv_samples"]
+    spmv_ms = (s1["spmv_sampled_ms"] - s0["spmv_sampled_ms"]) / max(n_s, 1)
+    spmv_bytes = 28 * slots + (16 + 16 + 1 + 0.25) * V_own
+    fine_ops = s1["fine_op_launches"] - s0["fine_op_launches"]
+    packed_ops = s1["packed_op_launches"] - s0["packed_op_launches"]
+    roof_jv = {
+        "bound": "hbm", "kernel": "k_block_op<0> (fp64 J*v and Krylov residual, 2x2-block sliced-ELL)",
+        "achieved": spmv_bytes / (spmv_ms * 1e-3) / 1e9 if n_s else None, "peak": peak, "unit": "GB/s",
+        "frac": spmv_bytes / (spmv_ms * 1e-3) / 1e9 / peak if n_s else None, "traffic": traffic_of("spmv_traffic.json"),
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms, "launches_sampled": n_s,
         "csr_equivalent_bytes": 12 * stats0["nnz"] + 16 * stats0["local_rows"] + 8 * (stats0["local_rows"] + 1),
-        # every fine-level application of the block operator (J*v, Krylov residual, smoother sweeps and
-        # residual of the multigrid cycle) is a launch of this kernel
-        "launches_in_timed_region": s1["fine_op_launches"] - s0["fine_op_launches"],
-        "share_of_step": (spmv_ms * (s1["fine_op_launches"] - s0["fine_op_launches"])) / (secs * 1e3) if secs > 0 else None,
+        "launches_in_timed_region": fine_ops - packed_ops,
+        "share_of_step": spmv_ms * (fine_ops - packed_ops) / (secs * 1e3) if secs > 0 else None,
     }
+    # (2) the multigrid cycle's fine-level sweep (k_packed_op, the dominant kernel with pc mg): 16-byte record per slot;
+    # per node: gathered v (16), b (16), node-block inverse (32), y (16), bc flag (1), slice ptr (8/32)
+    n_p = s1["smooth_samples"] - s0["smooth_samples"]
+    roofline = roof_jv
+    roof_extra = None
+    if n_p:
+        sm_ms = (s1["smooth_sampled_ms"] - s0["smooth_sampled_ms"]) / n_p
+        sm_bytes = 16 * slots + (16 + 16 + 32 + 16 + 1 + 0.25) * V_own
+        roofline = {
+            "bound": "hbm", "kernel": "k_packed_op (multigrid smoother sweep on the fine level: packed {col, alpha K, M, D} "
+                                      "single-precision records, fp64 accumulation, fused node-block Jacobi update)",
+            "achieved": sm_bytes / (sm_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": sm_bytes / (sm_ms * 1e-3) / 1e9 / peak,
+            "traffic": traffic_of("smooth_traffic.json"), "peak_source": peak_src, "algorithmic_bytes_per_launch": sm_bytes,
+            "ms_per_launch": sm_ms, "launches_sampled": n_p, "launches_in_timed_region": packed_ops,
+            "share_of_step": sm_ms * packed_ops / (secs * 1e3) if secs > 0 else None,
+        }
+        roof_extra = roof_jv
 
     # ---- e2e: the same solve through NonlinearProblem.solve() on host buffers (H2D of sol and sol_k,
     # D2H of sol inside the timed region), whole outer iterations until >= K Newton steps
@@ -308,18 +337,18 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": done, "warmup": args.warmup,
             "ms_per_step": 1e3 * secs / max(done, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"3-D P1 obstacle LVPP (configs[1]): {n}x{n}x{n * world} cubes x 6 tets, "
+            "config": {"workload": f"3-D P1 obstacle LVPP (configs[1]): {nxy}x{nxy}x{nz} cubes x 6 tets, "
                                    f"{rows_global} rows, {stats0['nnz']} nnz/GPU (CSR-equivalent)",
                        "n": n, "rows": rows_global, "alpha_scheme": "double_exponential", "alpha_max": 1e2,
                        "snes_rtol": 1e-6, "ksp": ("MINRES + block-Jacobi/Schur-diag" if args.pc == "jacobi" else
                                "GMRES(50) + monolithic aggregation multigrid V(2,2) (node-block Jacobi smoother)"), "ksp_rtol": args.ksp_rtol,
                        "l2": "operator (>=4 GB) and vectors exceed the 126 MB L2; no flush needed" if n >= 100 else
                              "inputs fit L2: kernel-level numbers are L2-warm",
-                       "parallelism": f"slab{world}",
-                       "obstacle": "phi_set of obstacle_pg.py:92-104" + (", one copy per slab (period 2 in z)" if world > 1 else "")},
+                       "parallelism": f"slab{world}", "weak_scaling": (None if world == 1 else args.weak),
+                       "obstacle": "phi_set of obstacle_pg.py:92-104" + (", one copy per slab (period 2 in z)" if slabs > 1 else "")},
             "newton_steps_per_sec": done / secs, "krylov_iterations": kry, "vcycles": s1["vcycles"] - s0["vcycles"],
             "mg_levels": s1["mg_levels"], "wall_s": wall, "setup_s": t_setup,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "roofline_jv": roof_extra, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "assembly": asm, "device_bytes": stats0["device_bytes"], "outer_history": st.history,
         }
         print(json.dumps(line))
@@ -405,6 +434,9 @@ def main():
                     help="jacobi: block-diagonal MINRES; mg: multigrid-preconditioned GMRES")
     ap.add_argument("--workload", default="obstacle", choices=["obstacle", "gradient", "multiphase", "signorini"],
                     help="obstacle (the driver's line, configs[1]) or one of the mixed-form examples (1 GPU, --size = N)")
+    ap.add_argument("--weak", default="refine", choices=["refine", "stack"],
+                    help="N > 1: refine the mesh of the one-obstacle problem (default) or stack N copies along z")
+    ap.add_argument("--slabs", type=int, default=1, help="1 GPU only: solve the global problem of an S-GPU run (diagnostic)")
     ap.add_argument("--skip-e2e", dest="no_e2e", action="store_true")
     ap.add_argument("--skip-cpu", dest="no_cpu", action="store_true")
     ap.add_argument("--skip-aux", dest="no_aux", action="store_true")

@@ -144,6 +144,10 @@ typedef struct lvpp_stats {
   int64_t vcycles;           /* cumulative multigrid V-cycles */
   int32_t mg_levels;         /* levels of the multigrid hierarchy (0 until first used) */
   int32_t reserved0;
+  double smooth_sampled_ms;  /* cumulative CUDA-event time of the sampled fine-level smoother sweeps of the multigrid
+                                cycle (packed single-precision operator, one sample per V-cycle of a Krylov solve) */
+  int64_t smooth_samples;    /* number of sampled smoother sweeps */
+  int64_t packed_op_launches;/* cumulative fine-level launches of the cycle's packed operator kernel */
 } lvpp_stats;
 
 const char* lvpp_last_error(void);

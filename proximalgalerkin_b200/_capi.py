@@ -154,6 +154,9 @@ class Stats(C.Structure):
         ("vcycles", C.c_int64),
         ("mg_levels", C.c_int32),
         ("reserved0", C.c_int32),
+        ("smooth_sampled_ms", C.c_double),
+        ("smooth_samples", C.c_int64),
+        ("packed_op_launches", C.c_int64),
     ]
 
     def as_dict(self):

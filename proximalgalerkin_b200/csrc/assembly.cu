@@ -474,7 +474,7 @@ static int assemble_D(lvpp_problem* h, const double* d_x) {
 static OpArgs op_args(lvpp_problem* h) {
   OpArgs p;
   p.Vown = h->Vown; p.slice_ptr = h->slice_ptr; p.col = h->col;
-  p.K = h->K; p.M = h->M; p.D = h->D; p.Kf = nullptr; p.Mf = nullptr; p.Df = nullptr; p.bc_flag = h->bc_flag; p.bc_val = h->bc_val;
+  p.K = h->K; p.M = h->M; p.D = h->D; p.bc_flag = h->bc_flag; p.bc_val = h->bc_val;
   p.alpha = h->alpha; p.v = nullptr; p.xk = (const double2*)h->xk; p.bobs = h->bobs; p.fvec = h->fvec;
   p.f = h->f; p.inv_scale = nullptr; p.skip_flag = nullptr; p.y = nullptr; p.partials = nullptr;
   p.epi = EPI_NONE; p.b = nullptr; p.binv = nullptr; p.omega = 1.0;

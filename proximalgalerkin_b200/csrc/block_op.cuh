@@ -8,8 +8,7 @@
 //                  Epilogue `epi`:  EPI_NONE   y = J v
 //                                   EPI_RESID  y = b - J v
 //                                   EPI_JACOBI y = v + omega * Binv (b - J v)   (damped node-block Jacobi)
-//                  F32: the values are read from single-precision copies (the multigrid cycle is a
-//                  preconditioner: its operator only has to be fixed, not exact; 16 instead of 28 bytes per slot)
+//                  (the multigrid cycle applies its own packed single-precision copy: k_packed_op below)
 //   MODE 1 (F):    residual of obstacle_pg.py:116-124 with apply_lifting(x0 = x, scale -1) and
 //                  set_bc(x, -1) (src/lvpp/problem.py:59-67): the linear part is evaluated at x with
 //                  its Dirichlet entries replaced by g, Dirichlet rows are x - g; fused partial ||F||^2.
@@ -23,7 +22,6 @@ struct OpArgs {
   const int64_t* slice_ptr;
   const uint32_t* col;
   const double *K, *M, *D;
-  const float *Kf, *Mf, *Df;  // F32 = true: single-precision copies of the values (multigrid smoother only)
   const uint8_t* bc_flag;
   const double* bc_val;
   double alpha;
@@ -42,7 +40,7 @@ struct OpArgs {
   double omega;
 };
 
-template <int MODE, bool F32 = false>
+template <int MODE>
 __global__ void __launch_bounds__(256) k_block_op(OpArgs p) {
   __shared__ double s_red[32];
   double part = 0.0;
@@ -60,8 +58,7 @@ __global__ void __launch_bounds__(256) k_block_op(OpArgs p) {
       for (int k = 0; k < w; ++k) {
         const int64_t idx = base + (int64_t)k * LVPP_SLICE;
         const uint32_t c = p.col[idx];
-        const double kv = F32 ? (double)p.Kf[idx] : p.K[idx], mv = F32 ? (double)p.Mf[idx] : p.M[idx],
-                     dv = F32 ? (double)p.Df[idx] : p.D[idx];
+        const double kv = p.K[idx], mv = p.M[idx], dv = p.D[idx];
         const uint32_t j = c & ~LVPP_COL_BC;
         double2 vj = __ldg(&p.v[j]);
         if (MODE == 0) {
@@ -108,10 +105,98 @@ __global__ void __launch_bounds__(256) k_block_op(OpArgs p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The multigrid cycle's copy of the operator: one 16-byte record {column | bc bit, float(alpha K), float(M),
+// float(D)} per sliced-ELL slot, so that a lane fetches a slot with ONE 128-bit load (a warp: 512 contiguous
+// bytes per k) instead of four 32-bit streams, and 16 instead of 28 bytes per slot cross HBM.  The cycle is a
+// preconditioner: its operator only has to be a fixed linear map, not the exact Jacobian; sums are still
+// accumulated in fp64.  The record stream of the next U slots is requested before the gathers of the current U
+// are issued (register double buffer): the two dependent memory phases (records, then v[col]) of consecutive
+// groups overlap, which is what the four-stream version lacked (ncu: 4.9 TB/s, no unit above 41 %).
+struct PackedOpArgs {
+  int64_t Vown;
+  const int64_t* slice_ptr;
+  const uint4* P;        // [slots]
+  const uint8_t* bc_flag;
+  const double2* v;
+  double2* y;
+  int epi;               // EPI_NONE / EPI_RESID / EPI_JACOBI
+  const double2* b;
+  const double* binv;    // [Vown * 4]
+  double omega;
+};
+
+// loads as volatile asm: the compiler otherwise sinks the next group's record loads below the current group's
+// arithmetic and serialises the gathers through one register quad (40 registers, one load in flight per thread)
+__device__ __forceinline__ uint4 lvpp_ld_record(const uint4* ptr) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(ptr));
+  return r;
+}
+__device__ __forceinline__ double2 lvpp_ld_pair(const double2* ptr) {
+  double2 r;
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(ptr));
+  return r;
+}
+
+template <int U, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_packed_op(PackedOpArgs p) {
+  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x; i0 < p.Vown; i0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = i0 + threadIdx.x;
+    if (i >= p.Vown) continue;
+    const int64_t s = i >> 5;
+    const int64_t b0 = p.slice_ptr[s];
+    const int w = (int)((p.slice_ptr[s + 1] - b0) >> 5);  // warp-uniform, >= 1 (every row holds its diagonal)
+    const uint4* q = p.P + b0 + (i & 31);
+    // slots past the end of the row re-read the last record (cache hit) and are zeroed: no predicated loads
+    uint4 cur[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) cur[u] = lvpp_ld_record(q + (int64_t)min(u, w - 1) * LVPP_SLICE);
+    double au = 0.0, ap = 0.0;
+    for (int k0 = 0; k0 < w; k0 += U) {
+      uint4 nxt[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) nxt[u] = lvpp_ld_record(q + (int64_t)min(k0 + U + u, w - 1) * LVPP_SLICE);
+      double2 vj[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) vj[u] = lvpp_ld_pair(&p.v[cur[u].x & ~LVPP_COL_BC]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool live = k0 + u < w;
+        const double kv = live ? (double)__uint_as_float(cur[u].y) : 0.0, mv = live ? (double)__uint_as_float(cur[u].z) : 0.0,
+                     dv = live ? (double)__uint_as_float(cur[u].w) : 0.0;
+        const double vx = (cur[u].x & LVPP_COL_BC) ? 0.0 : vj[u].x;
+        au += kv * vx + mv * vj[u].y;
+        ap += mv * vx - dv * vj[u].y;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+    }
+    const double2 vi = p.v[i];
+    const bool isbc = p.bc_flag[i] != 0;
+    double2 out;
+    out.x = isbc ? vi.x : au;
+    out.y = ap;
+    if (p.epi != EPI_NONE) {
+      const double2 bi = p.b[i];
+      const double ru = bi.x - out.x, rp = bi.y - out.y;
+      if (p.epi == EPI_RESID) {
+        out.x = ru;
+        out.y = rp;
+      } else {
+        const double* B = p.binv + 4 * i;
+        out.x = vi.x + (isbc ? 1.0 : p.omega) * (B[0] * ru + B[1] * rp);
+        out.y = vi.y + p.omega * (B[2] * ru + B[3] * rp);
+      }
+    }
+    p.y[i] = out;
+  }
+}
+
 static inline OpArgs lvpp_level_op(const lvpp_problem* h, const MgLevel& L) {
   OpArgs p;
   p.Vown = L.Vown; p.slice_ptr = L.slice_ptr; p.col = L.col;
-  p.K = L.K; p.M = L.M; p.D = L.D; p.Kf = L.Kf; p.Mf = L.Mf; p.Df = L.Df; p.bc_flag = L.bc_flag; p.bc_val = nullptr;
+  p.K = L.K; p.M = L.M; p.D = L.D; p.bc_flag = L.bc_flag; p.bc_val = nullptr;
   p.alpha = h->alpha; p.v = nullptr; p.xk = nullptr; p.bobs = nullptr; p.fvec = nullptr;
   p.f = 0.0; p.inv_scale = nullptr; p.skip_flag = nullptr; p.y = nullptr; p.partials = nullptr;
   p.epi = EPI_NONE; p.b = nullptr; p.binv = nullptr; p.omega = 1.0;

@@ -92,7 +92,7 @@ struct MgLevel {
   int32_t* rowlen = nullptr;
   uint8_t* diag_k = nullptr;
   double *K = nullptr, *M = nullptr, *D = nullptr;
-  float *Kf = nullptr, *Mf = nullptr, *Df = nullptr;  // single-precision copies read by the smoother sweeps
+  uint4* P = nullptr;            // packed single-precision copy {col, alpha K, M, D} read by the cycle (block_op.cuh)
   uint8_t* bc_flag = nullptr;    // [V] u dof of the node is inactive (Dirichlet / all-Dirichlet aggregate)
   int32_t* box = nullptr;        // [Vown * 3] integer box coordinates used by the coordinate aggregation
   // transfer to the next coarser level
@@ -109,6 +109,7 @@ struct MgLevel {
   double omega = 0.7;            // damping of the node-block Jacobi smoother on this level
   double sweep_omega[MG_MAX_SWEEPS] = {0};  // damping of sweep k of a smoothing step (Chebyshev roots or omega)
   double lambda = 0.0;           // last estimate of lambda_max(Binv J)
+  bool ev_valid = false;         // ev holds the vector of the previous estimate (warm start)
   LevelHalo halo;
 };
 
@@ -171,6 +172,11 @@ struct lvpp_problem {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs0 = nullptr, evs1 = nullptr, evt0 = nullptr, evt1 = nullptr;
   double spmv_sampled_ms = 0.0;
   int64_t spmv_samples = 0;
+  // one fine-level smoother sweep (k_packed_op, EPI_JACOBI) per V-cycle is bracketed by events (bench.py roofline)
+  cudaEvent_t evp0 = nullptr, evp1 = nullptr;
+  bool smooth_sample_pending = false, smooth_sample_recorded = false;
+  double smooth_sampled_ms = 0.0;
+  int64_t smooth_samples = 0, packed_op_launches = 0;
   // communication
   int rank = 0, nranks = 1;
   void* nccl_comm = nullptr;
@@ -183,12 +189,13 @@ struct lvpp_problem {
   double h0 = 0.0;                // node spacing used by the coordinate aggregation
   double xmin[3] = {0, 0, 0};
   int mg_nsmooth = 2;
-  bool mg_fp32 = true;            // smoother sweeps read single-precision copies of K, M, D
+  bool mg_fp32 = true;            // the cycle reads the packed single-precision copy of the operator
   // over-correction of the piecewise-constant coarse correction and relative damping of the smoother
   // (omega_l = mg_omega * 2 / (1.15 lambda_max)); tuned on the n = 215 obstacle problem (profiles/r01_mg_scan.txt)
   double mg_omega = 1.0, mg_over = 1.8;
-  double mg_margin = 1.15;        // safety factor on the power-iteration estimate of lambda_max(Binv J)
+  double mg_margin = 1.10;        // safety factor on the power-iteration estimate of lambda_max(Binv J)
   int mg_power_its = 10;
+  int mg_unroll = 4;              // slots per register buffer of k_packed_op (4 or 8)
   double mg_cheb = 10.0;          // > 1: Chebyshev-root damping of the sweeps over [b / mg_cheb, b]; else plain damping
   double mg_alpha_est = -1.0;     // alpha of the last smoother eigenvalue estimate
   double* coarse_lu = nullptr;    // dense inverse of the coarsest operator (all ranks' rows) [nc * nc]

@@ -20,6 +20,7 @@
 #include <cub/cub.cuh>
 
 #include <cmath>
+#include <cstring>
 
 #include "block_op.cuh"
 #include "gmres_kernels.cuh"
@@ -344,9 +345,13 @@ __global__ void k_coarse_apply(int n, int nloc, int row0, const double* __restri
   }
 }
 
-__global__ void k_to_float(int64_t n, const double* __restrict__ a, float* __restrict__ b) {
+// packed single-precision copy of a level's operator for the cycle (block_op.cuh: k_packed_op)
+__global__ void k_pack_op(int64_t n, const uint32_t* __restrict__ col, const double* __restrict__ K,
+                          const double* __restrict__ M, const double* __restrict__ D, double alpha,
+                          uint4* __restrict__ P) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    b[i] = (float)a[i];
+    P[i] = make_uint4(col[i], __float_as_uint((float)(alpha * K[i])), __float_as_uint((float)M[i]),
+                      __float_as_uint((float)D[i]));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -623,6 +628,7 @@ int lvpp_mg_setup(lvpp_problem* h) {
   h->mg_nsmooth = (int)env_double("LVPP_MG_NSMOOTH", h->mg_nsmooth);
   if (h->mg_nsmooth < 1 || h->mg_nsmooth > MG_MAX_SWEEPS) { lvpp_set_error("bad LVPP_MG_NSMOOTH"); return LVPP_E_INVALID; }
   h->mg_cheb = env_double("LVPP_MG_CHEB", h->mg_cheb);
+  h->mg_unroll = (int)env_double("LVPP_MG_UNROLL", h->mg_unroll);
   h->mg_margin = env_double("LVPP_MG_MARGIN", h->mg_margin);
   h->mg_power_its = (int)env_double("LVPP_MG_POWER_ITS", h->mg_power_its);
   h->gm_eta2 = env_double("LVPP_GMRES_ETA2", h->gm_eta2);
@@ -670,15 +676,7 @@ int lvpp_mg_setup(lvpp_problem* h) {
   }
   h->mg_fp32 = env_double("LVPP_MG_FP32", 1.0) != 0.0;
   if (h->mg_fp32)
-    for (size_t l = 0; l + 1 < h->levels.size(); ++l) {
-      MgLevel& L = h->levels[l];
-      CKR(lvpp_dalloc(h, &L.Kf, (size_t)L.slots, false));
-      CKR(lvpp_dalloc(h, &L.Mf, (size_t)L.slots, false));
-      CKR(lvpp_dalloc(h, &L.Df, (size_t)L.slots, false));
-      LAUNCH(h, k_to_float, lvpp_grid(L.slots, 256, 16), 256, 0, L.slots, L.K, L.Kf);
-      LAUNCH(h, k_to_float, lvpp_grid(L.slots, 256, 16), 256, 0, L.slots, L.M, L.Mf);
-      CK(cudaGetLastError());
-    }
+    for (size_t l = 0; l + 1 < h->levels.size(); ++l) CKR(lvpp_dalloc(h, &h->levels[l].P, (size_t)h->levels[l].slots, false));
   // coarsest level: global numbering of all ranks' coarse nodes, rank by rank
   const MgLevel& Lc = h->levels.back();
   std::vector<double> cnt((size_t)h->nranks, 0.0);
@@ -719,17 +717,32 @@ int lvpp_mg_setup(lvpp_problem* h) {
 
 static int level_op_local(lvpp_problem* h, MgLevel& L, int epi, double omega, const double* v, const double* b,
                          double* y, bool f32 = false) {
-  OpArgs p = lvpp_level_op(h, L);
-  p.v = (const double2*)v;
-  p.y = (double2*)y;
-  p.epi = epi;
-  p.b = (const double2*)b;
-  p.binv = L.binv;
-  p.omega = omega;
   const int grid = lvpp_grid(L.Vown, 256, 6);
   if (&L == &h->levels[0]) h->fine_op_launches++;
-  if (f32 && L.Kf) LAUNCH(h, (k_block_op<0, true>), grid, 256, 0, p);
-  else LAUNCH(h, (k_block_op<0, false>), grid, 256, 0, p);
+  if (f32 && L.P) {
+    PackedOpArgs q;
+    q.Vown = L.Vown; q.slice_ptr = L.slice_ptr; q.P = L.P; q.bc_flag = L.bc_flag;
+    q.v = (const double2*)v; q.y = (double2*)y; q.epi = epi; q.b = (const double2*)b; q.binv = L.binv; q.omega = omega;
+    const bool sample = &L == &h->levels[0] && epi == EPI_JACOBI && h->smooth_sample_pending;
+    if (sample) CK(cudaEventRecord(h->evp0, h->stream));
+    if (h->mg_unroll == 8) LAUNCH(h, (k_packed_op<8, 3>), lvpp_grid(L.Vown, 256, 3), 256, 0, q);
+    else LAUNCH(h, (k_packed_op<4, 4>), lvpp_grid(L.Vown, 256, 4), 256, 0, q);
+    if (&L == &h->levels[0]) h->packed_op_launches++;
+    if (sample) {
+      CK(cudaEventRecord(h->evp1, h->stream));
+      h->smooth_sample_pending = false;
+      h->smooth_sample_recorded = true;
+    }
+  } else {
+    OpArgs p = lvpp_level_op(h, L);
+    p.v = (const double2*)v;
+    p.y = (double2*)y;
+    p.epi = epi;
+    p.b = (const double2*)b;
+    p.binv = L.binv;
+    p.omega = omega;
+    LAUNCH(h, (k_block_op<0>), grid, 256, 0, p);
+  }
   CK(cudaGetLastError());
   return 0;
 }
@@ -749,12 +762,17 @@ static int build_binv(lvpp_problem* h, MgLevel& L) {
 }
 
 // lambda_max(Binv J) of one level by power iteration on I + Binv J (the Jacobi epilogue with b = 0 and
-// omega = -1) from a fixed start vector: the estimate depends only on the operator, never on history
+// omega = -1).  The norm growth of an unconverged vector is a LOWER estimate, so the first call on a level runs
+// three times as long from a fixed pseudo-random vector and later calls (alpha changed, the operator moved a
+// little) restart from the previous vector.  Everything is deterministic: the same solve gives the same estimates.
 static int estimate_lambda(lvpp_problem* h, MgLevel& L) {
   const int nb = h->npartials;
-  const int nit = h->mg_power_its;
-  LAUNCH(h, k_ev_init, lvpp_grid(L.Vown, 256, 8), 256, 0, L.Vown, (double2*)L.ev);
-  CK(cudaGetLastError());
+  const int nit = L.ev_valid ? h->mg_power_its : 3 * h->mg_power_its;
+  if (!L.ev_valid) {
+    LAUNCH(h, k_ev_init, lvpp_grid(L.Vown, 256, 8), 256, 0, L.Vown, (double2*)L.ev);
+    CK(cudaGetLastError());
+  }
+  L.ev_valid = true;
   CK(cudaMemsetAsync(L.x, 0, sizeof(double) * 2 * L.V, h->stream));
   double lam = 0.0;
   for (int it = 0; it <= nit; ++it) {
@@ -792,30 +810,31 @@ int lvpp_mg_update(lvpp_problem* h) {
   if (h->mg_fp32)
     for (int l = 0; l + 1 < nl; ++l) {
       MgLevel& L = h->levels[l];
-      LAUNCH(h, k_to_float, lvpp_grid(L.slots, 256, 16), 256, 0, L.slots, L.D, L.Df);
+      LAUNCH(h, k_pack_op, lvpp_grid(L.slots, 256, 16), 256, 0, L.slots, L.col, L.K, L.M, L.D, h->alpha, L.P);
       CK(cudaGetLastError());
     }
-  // Damping: lambda_max(Binv J) is set by the stiffness block (mesh and element, not psi), so it is estimated
-  // when alpha changes (once per proximal step) with a 15 % margin for its drift over the Newton steps.
+  // lambda_max(Binv J) is set by the stiffness block (mesh and element, much less by psi), so it is estimated when
+  // alpha changes (once per proximal step), with a margin for the estimate's deficit and its drift over the Newton
+  // steps.
   const bool estimate = !(h->mg_alpha_est == h->alpha);
   for (int l = 0; l + 1 < nl; ++l) {
     MgLevel& L = h->levels[l];
     CKR(build_binv(h, L));
-    if (estimate) {
-      CKR(estimate_lambda(h, L));
-      L.omega = h->mg_omega * std::min(1.0, 2.0 / (h->mg_margin * L.lambda));
-      // sweep k of a smoothing step is damped by omega_k.  Plain damped Jacobi: omega_k = omega.  Chebyshev
-      // (mg_cheb = ratio > 1): 1 / omega_k are the roots of the degree-nsmooth Chebyshev polynomial of the
-      // interval [b / ratio, b], b = 1.15 lambda_max -- the sweeps are the same kernel at the same cost, their
-      // product is the polynomial that is smallest on the upper part of the spectrum
-      const int m = h->mg_nsmooth;
-      for (int k = 0; k < m; ++k) {
-        if (h->mg_cheb > 1.0) {
-          const double b = h->mg_margin * L.lambda, a = b / h->mg_cheb;
-          L.sweep_omega[k] = 1.0 / (0.5 * (b + a) + 0.5 * (b - a) * cos(M_PI * (2 * k + 1) / (2.0 * m)));
-        } else {
-          L.sweep_omega[k] = L.omega;
-        }
+    if (!estimate) continue;
+    CKR(estimate_lambda(h, L));
+    // sweep k of a smoothing step is damped by omega_k.  Plain damped Jacobi: omega_k = omega.  Chebyshev
+    // (mg_cheb = ratio > 1): 1 / omega_k are the roots of the degree-nsmooth Chebyshev polynomial of the
+    // interval [b / ratio, b], b = margin * lambda_max -- the sweeps are the same kernel at the same cost, their
+    // product is the polynomial that is smallest on the upper part of the spectrum.  An eigenvalue above b is
+    // amplified, which is why the estimate is warm-started and carries a margin.
+    L.omega = h->mg_omega * std::min(1.0, 2.0 / (h->mg_margin * L.lambda));
+    const int m = h->mg_nsmooth;
+    for (int k = 0; k < m; ++k) {
+      if (h->mg_cheb > 1.0) {
+        const double b = h->mg_margin * L.lambda, a = b / h->mg_cheb;
+        L.sweep_omega[k] = 1.0 / (0.5 * (b + a) + 0.5 * (b - a) * cos(M_PI * (2 * k + 1) / (2.0 * m)));
+      } else {
+        L.sweep_omega[k] = L.omega;
       }
     }
   }
@@ -960,7 +979,10 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
     for (; j < m; ++j) {
       // w = J M^-1 v_j  -> stored in v_{j+1}
       double* z = nullptr;
+      h->smooth_sample_pending = true;
+      h->smooth_sample_recorded = false;
       CKR(lvpp_mg_vcycle(h, vec(j), &z));
+      h->smooth_sample_pending = false;
       if (h->nranks > 1) CKR(lvpp_halo_forward_level(h, h->halo, z));
       CK(cudaEventRecord(h->evs0, h->stream));
       CKR(level_op_local(h, L0, EPI_NONE, 1.0, z, nullptr, vec(j + 1)));
@@ -987,6 +1009,12 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
           CK(cudaEventElapsedTime(&sms, h->evs0, h->evs1));
           h->spmv_sampled_ms += sms;
           h->spmv_samples++;
+          if (h->smooth_sample_recorded) {
+            CK(cudaEventElapsedTime(&sms, h->evp0, h->evp1));
+            h->smooth_sampled_ms += sms;
+            h->smooth_samples++;
+            h->smooth_sample_recorded = false;
+          }
         }
         // selective re-orthogonalisation (Daniel et al.): only when the projection removed most of w
         if (beta * beta > h->gm_eta2 * (hsq + beta * beta)) break;

@@ -370,6 +370,8 @@ extern "C" int lvpp_create(const lvpp_obstacle_desc* d, lvpp_handle* out) {
     CK(cudaEventCreate(&h->ev1));
     CK(cudaEventCreate(&h->evs0));
     CK(cudaEventCreate(&h->evs1));
+    CK(cudaEventCreate(&h->evp0));
+    CK(cudaEventCreate(&h->evp1));
     CK(cudaEventCreate(&h->evt0));
     CK(cudaEventCreate(&h->evt1));
     h->tdim = d->tdim; h->nld = d->nld; h->nq = d->nq;
@@ -511,6 +513,8 @@ extern "C" int lvpp_destroy(lvpp_handle h) {
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->evs0) cudaEventDestroy(h->evs0);
   if (h->evs1) cudaEventDestroy(h->evs1);
+  if (h->evp0) cudaEventDestroy(h->evp0);
+  if (h->evp1) cudaEventDestroy(h->evp1);
   if (h->evt0) cudaEventDestroy(h->evt0);
   if (h->evt1) cudaEventDestroy(h->evt1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -536,6 +540,9 @@ extern "C" int lvpp_get_stats(lvpp_handle h, lvpp_stats* s) {
   s->spmv_sampled_ms = h->spmv_sampled_ms;
   s->spmv_samples = h->spmv_samples;
   s->fine_op_launches = h->fine_op_launches;
+  s->smooth_sampled_ms = h->smooth_sampled_ms;
+  s->smooth_samples = h->smooth_samples;
+  s->packed_op_launches = h->packed_op_launches;
   s->vcycles = h->vcycles;
   s->mg_levels = (int32_t)h->levels.size();
   s->reserved0 = 0;
