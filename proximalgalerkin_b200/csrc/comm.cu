@@ -135,13 +135,30 @@ int lvpp_allreduce_sum(lvpp_problem* h, double* d_buf, int n) {
 }
 
 // ---- peer-memory halo (NVLink / NVSwitch, no NCCL call on the solve path) ---------------------------
-// pack: gather the send list and store it into the neighbour's receive buffer; the last block to finish
-// raises the neighbour's flag to `seq` (system-scope release)
-__global__ void __launch_bounds__(256) k_pack_p2p(int64_t n, const int32_t* __restrict__ nodes, const double2* __restrict__ v,
-                                                   double2* __restrict__ peer_buf, int* __restrict__ counter,
-                                                   volatile unsigned long long* peer_flag, unsigned long long seq) {
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
-    peer_buf[p] = v[nodes[p]];
+// ONE kernel per exchange.  Phase 1 (push): gather the send lists and store them straight into the neighbours'
+// receive buffers over NVLink; the last block to finish raises every neighbour's flag to `seq` (system-scope
+// release).  Phase 2 (pull): wait until every neighbour has raised this rank's flags to `seq` (system-scope
+// acquire), then scatter the receive buffer (read past L1: the lines were written by a peer) into the ghost
+// entries.  The grid never exceeds one block per SM, so every block is resident and the wait of phase 2 cannot
+// starve a phase-1 block of this or of the neighbour's kernel.
+#define LVPP_MAX_NEIGHBORS 8
+struct HaloPush {
+  int nb;
+  int64_t send_ptr[LVPP_MAX_NEIGHBORS + 1];
+  double2* peer_buf[LVPP_MAX_NEIGHBORS];
+  unsigned long long* peer_flag[LVPP_MAX_NEIGHBORS];
+};
+
+__global__ void __launch_bounds__(256) k_halo_p2p(HaloPush hp, const int32_t* __restrict__ send_nodes,
+                                                   const int32_t* __restrict__ recv_nodes, int64_t nrecv, double2* __restrict__ v,
+                                                   const double2* __restrict__ rbuf, volatile unsigned long long* flags,
+                                                   int* __restrict__ counter, unsigned long long seq, int* __restrict__ err) {
+  const int64_t nsend = hp.send_ptr[hp.nb];
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nsend; p += (int64_t)gridDim.x * blockDim.x) {
+    int b = 0;
+    while (p >= hp.send_ptr[b + 1]) ++b;
+    hp.peer_buf[b][p - hp.send_ptr[b]] = v[send_nodes[p]];
+  }
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -149,17 +166,9 @@ __global__ void __launch_bounds__(256) k_pack_p2p(int64_t n, const int32_t* __re
     if (done == (int)gridDim.x - 1) {
       *counter = 0;
       __threadfence_system();
-      *peer_flag = seq;
+      for (int b = 0; b < hp.nb; ++b) *(volatile unsigned long long*)hp.peer_flag[b] = seq;
     }
-  }
-}
-// unpack: wait until every neighbour has raised its flag to `seq` (system-scope acquire), then scatter the
-// receive buffer (read past L1: the lines were written by a peer) into the ghost entries
-__global__ void __launch_bounds__(256) k_unpack_p2p(int64_t n, const int32_t* __restrict__ nodes, const double2* __restrict__ buf,
-                                                     double2* __restrict__ v, volatile unsigned long long* flags, int nflags,
-                                                     unsigned long long seq, int* __restrict__ err) {
-  if (threadIdx.x == 0) {
-    for (int b = 0; b < nflags; ++b) {
+    for (int b = 0; b < hp.nb; ++b) {
       const long long t0 = clock64();
       while (flags[b] < seq)
         if (clock64() - t0 > (1LL << 34)) {  // ~8 s: a peer died or the call sequences diverged
@@ -170,8 +179,8 @@ __global__ void __launch_bounds__(256) k_unpack_p2p(int64_t n, const int32_t* __
     __threadfence_system();
   }
   __syncthreads();
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
-    v[nodes[p]] = __ldcg(&buf[p]);
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nrecv; p += (int64_t)gridDim.x * blockDim.x)
+    v[recv_nodes[p]] = __ldcg(&rbuf[p]);
 }
 
 struct P2pHello {  // what a rank tells each neighbour about its receive arena
@@ -195,7 +204,7 @@ int lvpp_halo_p2p_setup(lvpp_problem* h, LevelHalo& H) {
     if (cudaHostAlloc((void**)&h->p2p_err, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) ok = 0;
     else *h->p2p_err = 0;
   }
-  if (ok && nb * sizeof(unsigned long long) > flag_bytes) ok = 0;
+  if (ok && nb > LVPP_MAX_NEIGHBORS) ok = 0;
   P2pHello mine;
   memset(&mine, 0, sizeof(mine));
   if (ok) {
@@ -263,14 +272,20 @@ int lvpp_halo_p2p_setup(lvpp_problem* h, LevelHalo& H) {
 static int halo_forward_p2p(lvpp_problem* h, LevelHalo& H, double* d_v) {
   const unsigned long long seq = ++H.seq;
   const int par = (int)(seq & 1);
+  HaloPush hp;
+  hp.nb = H.num_neighbors;
   for (int b = 0; b < H.num_neighbors; ++b) {
-    const int64_t s0 = H.send_ptr[b], n = H.send_ptr[b + 1] - s0;
-    LAUNCH(h, k_pack_p2p, lvpp_grid(n, 256, 2), 256, 0, n, H.send_nodes + s0, (const double2*)d_v,
-           (double2*)H.peer_rbuf[par][b], H.counters + b, H.peer_flag[b], seq);
+    hp.send_ptr[b] = H.send_ptr[b];
+    hp.peer_buf[b] = (double2*)H.peer_rbuf[par][b];
+    hp.peer_flag[b] = H.peer_flag[b];
   }
-  const int64_t nr = H.recv_ptr.back();
-  LAUNCH(h, k_unpack_p2p, lvpp_grid(nr, 256, 2), 256, 0, nr, H.recv_nodes, (const double2*)H.rbuf[par], (double2*)d_v,
-         H.flags, H.num_neighbors, seq, h->p2p_err);
+  hp.send_ptr[H.num_neighbors] = H.send_ptr[H.num_neighbors];
+  const int64_t nr = H.recv_ptr.back(), ns = H.send_ptr.back();
+  int64_t blocks = (std::max(nr, ns) + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > LVPP_NUM_SMS) blocks = LVPP_NUM_SMS;  // all blocks resident: see k_halo_p2p
+  LAUNCH(h, k_halo_p2p, (int)blocks, 256, 0, hp, H.send_nodes, H.recv_nodes, nr, (double2*)d_v, (const double2*)H.rbuf[par],
+         H.flags, H.counters, seq, h->p2p_err);
   CK(cudaGetLastError());
   return 0;
 }
