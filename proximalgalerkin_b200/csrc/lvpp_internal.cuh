@@ -107,7 +107,8 @@ struct MgLevel {
   double *b = nullptr, *x = nullptr, *t = nullptr;
   double* ev = nullptr;          // [2V] power-iteration vector (lambda_max of Binv J, kept between updates)
   double omega = 0.7;            // damping of the node-block Jacobi smoother on this level
-  double sweep_omega[MG_MAX_SWEEPS] = {0};  // damping of sweep k of a smoothing step (Chebyshev roots or omega)
+  double sweep_omega[MG_MAX_SWEEPS] = {0};      // damping of post-smoothing sweep k (Chebyshev roots or omega)
+  double sweep_omega_pre[MG_MAX_SWEEPS] = {0};  // same for the pre-smoothing sweeps
   double lambda = 0.0;           // last estimate of lambda_max(Binv J)
   bool ev_valid = false;         // ev holds the vector of the previous estimate (warm start)
   LevelHalo halo;
@@ -189,6 +190,7 @@ struct lvpp_problem {
   double h0 = 0.0;                // node spacing used by the coordinate aggregation
   double xmin[3] = {0, 0, 0};
   int mg_nsmooth = 2;
+  int mg_npre = 2, mg_npost = 2;  // sweeps before / after the coarse-grid correction (LVPP_MG_NSMOOTH sets both)
   bool mg_fp32 = true;            // the cycle reads the packed single-precision copy of the operator
   // over-correction of the piecewise-constant coarse correction and relative damping of the smoother
   // (omega_l = mg_omega * 2 / (1.15 lambda_max)); tuned on the n = 215 obstacle problem (profiles/r01_mg_scan.txt)

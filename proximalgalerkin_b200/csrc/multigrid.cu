@@ -627,6 +627,12 @@ int lvpp_mg_setup(lvpp_problem* h) {
   h->mg_omega = env_double("LVPP_MG_OMEGA", h->mg_omega);
   h->mg_nsmooth = (int)env_double("LVPP_MG_NSMOOTH", h->mg_nsmooth);
   if (h->mg_nsmooth < 1 || h->mg_nsmooth > MG_MAX_SWEEPS) { lvpp_set_error("bad LVPP_MG_NSMOOTH"); return LVPP_E_INVALID; }
+  h->mg_npre = (int)env_double("LVPP_MG_NPRE", getenv("LVPP_MG_NSMOOTH") ? h->mg_nsmooth : h->mg_npre);
+  h->mg_npost = (int)env_double("LVPP_MG_NPOST", getenv("LVPP_MG_NSMOOTH") ? h->mg_nsmooth : h->mg_npost);
+  if (h->mg_npre < 0 || h->mg_npre > MG_MAX_SWEEPS || h->mg_npost < 1 || h->mg_npost > MG_MAX_SWEEPS) {
+    lvpp_set_error("bad LVPP_MG_NPRE / LVPP_MG_NPOST");
+    return LVPP_E_INVALID;
+  }
   h->mg_cheb = env_double("LVPP_MG_CHEB", h->mg_cheb);
   h->mg_unroll = (int)env_double("LVPP_MG_UNROLL", h->mg_unroll);
   h->mg_margin = env_double("LVPP_MG_MARGIN", h->mg_margin);
@@ -828,13 +834,16 @@ int lvpp_mg_update(lvpp_problem* h) {
     // product is the polynomial that is smallest on the upper part of the spectrum.  An eigenvalue above b is
     // amplified, which is why the estimate is warm-started and carries a margin.
     L.omega = h->mg_omega * std::min(1.0, 2.0 / (h->mg_margin * L.lambda));
-    const int m = h->mg_nsmooth;
-    for (int k = 0; k < m; ++k) {
-      if (h->mg_cheb > 1.0) {
-        const double b = h->mg_margin * L.lambda, a = b / h->mg_cheb;
-        L.sweep_omega[k] = 1.0 / (0.5 * (b + a) + 0.5 * (b - a) * cos(M_PI * (2 * k + 1) / (2.0 * m)));
-      } else {
-        L.sweep_omega[k] = L.omega;
+    for (int side = 0; side < 2; ++side) {  // pre- and post-smoothing polynomials may have different degrees
+      const int m = side == 0 ? h->mg_npre : h->mg_npost;
+      double* om = side == 0 ? L.sweep_omega_pre : L.sweep_omega;
+      for (int k = 0; k < m; ++k) {
+        if (h->mg_cheb > 1.0) {
+          const double b = h->mg_margin * L.lambda, a = b / h->mg_cheb;
+          om[k] = 1.0 / (0.5 * (b + a) + 0.5 * (b - a) * cos(M_PI * (2 * k + 1) / (2.0 * m)));
+        } else {
+          om[k] = L.omega;
+        }
       }
     }
   }
@@ -842,7 +851,7 @@ int lvpp_mg_update(lvpp_problem* h) {
   if (estimate && getenv("LVPP_MG_VERBOSE") && h->rank == 0) {
     fprintf(stderr, "[lvpp mg] lambda_max / omega:");
     for (int l = 0; l + 1 < nl; ++l)
-      fprintf(stderr, " %.3f/%.3f,%.3f", h->levels[l].lambda, h->levels[l].sweep_omega[0], h->levels[l].sweep_omega[h->mg_nsmooth - 1]);
+      fprintf(stderr, " %.3f/%.3f,%.3f", h->levels[l].lambda, h->levels[l].sweep_omega[0], h->levels[l].sweep_omega[h->mg_npost - 1]);
     fprintf(stderr, "\n");
   }
   MgLevel& Lc = h->levels.back();
@@ -875,21 +884,27 @@ int lvpp_mg_vcycle(lvpp_problem* h, const double* b_in, double** z_out) {
   const int nl = (int)h->levels.size();
   std::vector<double*> cur(nl), oth(nl);
   std::vector<const double*> rhs(nl);
-  const int nsm = h->mg_nsmooth;
+  const int npre = h->mg_npre, npost = h->mg_npost;
   rhs[0] = b_in;
   for (int l = 0; l < nl - 1; ++l) {
     MgLevel& L = h->levels[l];
     cur[l] = L.x; oth[l] = L.t;
-    LAUNCH(h, k_smooth_first, lvpp_grid(L.Vown, 256, 6), 256, 0, L.Vown, (const double2*)rhs[l], L.binv, L.bc_flag,
-           L.sweep_omega[0], (double2*)cur[l]);
-    CK(cudaGetLastError());
-    for (int s = 1; s < nsm; ++s) {
-      CKR(level_op(h, L, EPI_JACOBI, L.sweep_omega[s], cur[l], rhs[l], oth[l]));
-      std::swap(cur[l], oth[l]);
+    const double* res = rhs[l];  // no pre-smoothing: the iterate is zero and the residual is the right-hand side
+    if (npre == 0) {
+      CK(cudaMemsetAsync(cur[l], 0, sizeof(double) * 2 * L.Vown, h->stream));
+    } else {
+      LAUNCH(h, k_smooth_first, lvpp_grid(L.Vown, 256, 6), 256, 0, L.Vown, (const double2*)rhs[l], L.binv, L.bc_flag,
+             L.sweep_omega_pre[0], (double2*)cur[l]);
+      CK(cudaGetLastError());
+      for (int s = 1; s < npre; ++s) {
+        CKR(level_op(h, L, EPI_JACOBI, L.sweep_omega_pre[s], cur[l], rhs[l], oth[l]));
+        std::swap(cur[l], oth[l]);
+      }
+      CKR(level_op(h, L, EPI_RESID, L.omega, cur[l], rhs[l], oth[l]));  // residual into the spare buffer
+      res = oth[l];
     }
-    CKR(level_op(h, L, EPI_RESID, L.omega, cur[l], rhs[l], oth[l]));  // residual into the spare buffer
     MgLevel& C = h->levels[l + 1];
-    LAUNCH(h, k_restrict, lvpp_grid(C.Vown, 256, 6), 256, 0, C.Vown, L.agg_ptr, L.agg_members, (const double2*)oth[l],
+    LAUNCH(h, k_restrict, lvpp_grid(C.Vown, 256, 6), 256, 0, C.Vown, L.agg_ptr, L.agg_members, (const double2*)res,
            C.bc_flag, (double2*)C.b);
     CK(cudaGetLastError());
     rhs[l + 1] = C.b;
@@ -916,7 +931,7 @@ int lvpp_mg_vcycle(lvpp_problem* h, const double* b_in, double** z_out) {
     LAUNCH(h, k_prolong_add, lvpp_grid(L.Vown, 256, 6), 256, 0, L.Vown, L.agg, (const double2*)cur[l + 1], L.bc_flag,
            h->mg_over, (double2*)cur[l]);
     CK(cudaGetLastError());
-    for (int s = 0; s < nsm; ++s) {
+    for (int s = 0; s < npost; ++s) {
       CKR(level_op(h, L, EPI_JACOBI, L.sweep_omega[s], cur[l], rhs[l], oth[l]));
       std::swap(cur[l], oth[l]);
     }
