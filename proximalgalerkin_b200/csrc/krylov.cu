@@ -222,9 +222,24 @@ int lvpp_minres(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_ne
 int lvpp_solve_linear(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_newton_opts* o, int32_t* its,
                       int32_t* reason, double* rnorm) {
   if (o->pc_type == LVPP_PC_MG) {
-    if (o->pc_degree > 0) h->mg_nsmooth = o->pc_degree;
+    if (o->pc_degree > 0 && (h->mg_npre != o->pc_degree || h->mg_npost != o->pc_degree)) {
+      h->mg_nsmooth = h->mg_npre = h->mg_npost = o->pc_degree;
+      h->mg_alpha_est = -1.0;  // the sweep dampings depend on the degree
+    }
     CKR(lvpp_mg_update(h));
-    return lvpp_gmres_mg(h, d_rhs, d_y, o, its, reason, rnorm);
+    int32_t its1 = 0, reason1 = 0;
+    CKR(lvpp_gmres_mg(h, d_rhs, d_y, o, &its1, &reason1, rnorm));
+    if (reason1 < 0) {
+      // the Chebyshev sweeps amplify eigenvalues above their interval: a diverged / stagnated solve is retried once
+      // with eigenvalue estimates redone from scratch
+      int32_t its2 = 0;
+      CKR(lvpp_mg_reestimate(h));
+      CKR(lvpp_gmres_mg(h, d_rhs, d_y, o, &its2, &reason1, rnorm));
+      its1 += its2;
+    }
+    if (its) *its = its1;
+    if (reason) *reason = reason1;
+    return 0;
   }
   CKR(lvpp_build_preconditioner(h, o));
   return lvpp_minres(h, d_rhs, d_y, o, its, reason, rnorm);

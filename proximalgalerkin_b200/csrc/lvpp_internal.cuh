@@ -197,6 +197,8 @@ struct lvpp_problem {
   double mg_omega = 1.0, mg_over = 1.8;
   double mg_margin = 1.10;        // safety factor on the power-iteration estimate of lambda_max(Binv J)
   int mg_power_its = 10;
+  int mg_power_boost = 1;         // multiplier of the power iterations (10 while re-estimating after a failed solve)
+  int64_t mg_retries = 0;         // Krylov solves repeated after a re-estimate
   int mg_unroll = 4;              // slots per register buffer of k_packed_op (4 or 8)
   double mg_cheb = 10.0;          // > 1: Chebyshev-root damping of the sweeps over [b / mg_cheb, b]; else plain damping
   double mg_alpha_est = -1.0;     // alpha of the last smoother eigenvalue estimate
@@ -334,6 +336,7 @@ int lvpp_build_preconditioner(lvpp_problem* h, const lvpp_newton_opts* o);  // k
 void lvpp_comm_destroy(lvpp_problem* h);
 int lvpp_mg_setup(lvpp_problem* h);                                  // multigrid.cu
 int lvpp_mg_update(lvpp_problem* h);                                 // multigrid.cu
+int lvpp_mg_reestimate(lvpp_problem* h);                             // multigrid.cu
 int lvpp_mg_vcycle(lvpp_problem* h, const double* b_in, double** z_out);  // multigrid.cu
 int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_newton_opts* o, int32_t* its,
                   int32_t* reason, double* rnorm);                   // multigrid.cu

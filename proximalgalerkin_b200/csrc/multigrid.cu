@@ -349,9 +349,12 @@ __global__ void k_coarse_apply(int n, int nloc, int row0, const double* __restri
 __global__ void k_pack_op(int64_t n, const uint32_t* __restrict__ col, const double* __restrict__ K,
                           const double* __restrict__ M, const double* __restrict__ D, double alpha,
                           uint4* __restrict__ P) {
+  // D = int exp(psi) phi_i phi_j can exceed the single-precision range while Newton overshoots (psi > 88 + ln(1/M_ii)):
+  // clamp instead of producing inf (inf * 0 = NaN would poison the whole cycle)
+  const double big = 3.0e38;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    P[i] = make_uint4(col[i], __float_as_uint((float)(alpha * K[i])), __float_as_uint((float)M[i]),
-                      __float_as_uint((float)D[i]));
+    P[i] = make_uint4(col[i], __float_as_uint((float)fmin(fmax(alpha * K[i], -big), big)), __float_as_uint((float)M[i]),
+                      __float_as_uint((float)fmin(D[i], big)));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -773,7 +776,7 @@ static int build_binv(lvpp_problem* h, MgLevel& L) {
 // little) restart from the previous vector.  Everything is deterministic: the same solve gives the same estimates.
 static int estimate_lambda(lvpp_problem* h, MgLevel& L) {
   const int nb = h->npartials;
-  const int nit = L.ev_valid ? h->mg_power_its : 3 * h->mg_power_its;
+  const int nit = (L.ev_valid ? h->mg_power_its : 3 * h->mg_power_its) * h->mg_power_boost;
   if (!L.ev_valid) {
     LAUNCH(h, k_ev_init, lvpp_grid(L.Vown, 256, 8), 256, 0, L.Vown, (double2*)L.ev);
     CK(cudaGetLastError());
@@ -799,8 +802,29 @@ static int estimate_lambda(lvpp_problem* h, MgLevel& L) {
     CKR(level_op(h, L, EPI_JACOBI, -1.0, L.ev, L.x, L.t));
     std::swap(L.ev, L.t);
   }
-  L.lambda = lam;
+  // lambda_max(Binv J) is set by the stiffness block -- mesh and element -- and moves by a few per cent over a
+  // whole LVPP solve (2.37 - 2.49 on a 12 x 12 x 16 mesh with 200 iterations per estimate), while the power
+  // iteration converges ever more slowly once exp(psi) varies over many orders of magnitude (the estimate at the
+  // second proximal step of the n = 368 solve fell from 2.41 to 1.34 and the Chebyshev sweeps diverged).  The
+  // estimate is therefore monotone per handle: an over-estimate only makes the polynomial a little less sharp.
+  L.lambda = std::max(L.lambda, lam);
   return 0;
+}
+
+// after a failed Krylov solve: forget the eigenvalue estimates and redo them from the fixed start vector with ten
+// times the iterations (krylov.cu retries the solve once)
+int lvpp_mg_reestimate(lvpp_problem* h) {
+  for (MgLevel& L : h->levels) {
+    L.ev_valid = false;
+    L.lambda = 0.0;
+  }
+  h->mg_alpha_est = -1.0;
+  h->mg_power_boost = 10;
+  const int r = lvpp_mg_update(h);
+  h->mg_power_boost = 1;
+  h->mg_retries++;
+  if (getenv("LVPP_MG_VERBOSE") && h->rank == 0) fprintf(stderr, "[lvpp mg] Krylov solve failed: eigenvalue estimates redone, retrying\n");
+  return r;
 }
 
 // per Newton step: coarse D, damping, node-block inverses, dense inverse of the coarsest operator

@@ -64,3 +64,28 @@ def test_full_lvpp_solve_mg_matches_oracle(lib, kind, n, degree):
     assert np.linalg.norm(u - uo) / np.linalg.norm(uo) < 1e-10
     for key in ("energy", "complementarity", "feasibility", "dual_feasibility", "primal_increment", "latent_increment"):
         assert np.allclose(h[key], ho[key], rtol=1e-7, atol=1e-12), key
+
+
+@pytest.mark.parametrize("env", [{"LVPP_MG_CHEB": "0"}, {"LVPP_MG_FP32": "0"}, {"LVPP_MG_UNROLL": "8"},
+                                 {"LVPP_MG_NPRE": "1", "LVPP_MG_NPOST": "3"}])
+def test_mg_variants_solve_the_same_system(lib, env, monkeypatch):
+    """The tunables of the cycle (plain damping instead of Chebyshev roots, fp64 instead of the packed
+    single-precision operator, the other unroll of k_packed_op, unequal pre/post degrees) change the
+    preconditioner, never the solution: read at lvpp_mg_setup time, i.e. per handle."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    lvpp, s, dev, orc = _pair("tet", 9, 1)
+    rng = np.random.default_rng(3)
+    x = 0.2 * rng.standard_normal(orc.num_rows)
+    x[orc.bc_dofs] = 0.0
+    dev.set_alpha(3.0)
+    dev.set_previous(np.zeros(orc.num_rows))
+    X, R, Y = (lvpp.DeviceVector(dev.n, dev.device) for _ in range(3))
+    X.set(x)
+    dev.assemble_jacobian(X)
+    rhs = rng.standard_normal(orc.num_rows)
+    R.set(rhs)
+    its, reason, _ = dev.linear_solve(R, Y, lvpp.newton_options(dict(MG, ksp_rtol=1e-12)))
+    assert reason > 0 and its < 80, (its, reason)
+    ye = spla.splu(orc.jacobian(x, 3.0).tocsc()).solve(rhs)
+    assert np.linalg.norm(Y.numpy() - ye) / np.linalg.norm(ye) < 1e-8

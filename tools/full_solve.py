@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Full LVPP obstacle solve (all proximal steps, the reference's CI parameters) at a given size on one
+GPU or under torchrun; prints one JSON line with the iteration history, time and memory.
+
+  python tools/full_solve.py --size 368            # 100.5 M rows on one B200
+"""
+import argparse
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--size", type=int, default=215)
+    ap.add_argument("--pc", default="mg")
+    ap.add_argument("--verbose", action="store_true")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+
+    import proximalgalerkin_b200 as lvpp
+
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+    n = args.size
+    nz = world * max(2, round(n / world))
+    t0 = time.perf_counter()
+    msh = lvpp.mesh.create_box(n, n, nz, rank=rank, nranks=world)
+    opts = {"ksp_rtol": 1e-12, "ksp_type": "gmres", "pc_type": "mg"} if args.pc == "mg" else {"ksp_rtol": 1e-12}
+    st = lvpp.obstacle_pg.LvppStepper(msh, 1, "double_exponential", 1e2, 1e-4, petsc_options=opts)
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    if args.verbose and rank == 0:  # log every Newton step: norms, Krylov iterations and reason
+        inner = st.dev.newton_step
+
+        def logged(x, opts):
+            out = inner(x, opts)
+            (fnorm, ynorm, xnorm), kits, kreason = out
+            print(f"outer {st.k} alpha {st.alpha_value:.4g} newton {st.newton_its + 1}: |F| {fnorm:.3e} |y| {ynorm:.3e} "
+                  f"|x| {xnorm:.3e} krylov {kits} ({kreason})", file=sys.stderr, flush=True)
+            return out
+
+        st.dev.newton_step = logged
+    while st.step():
+        pass
+    torch.cuda.synchronize()
+    t_solve = time.perf_counter() - t1
+    s = st.dev.stats()
+    if rank == 0:
+        print(json.dumps({
+            "workload": f"3-D P1 obstacle LVPP, {n}x{n}x{nz} cubes x 6 tets, full solve (double-exponential alpha, alpha_max 1e2, tol 1e-4)",
+            "n_gpus": world, "rows": s["num_rows"], "setup_s": t_setup, "solve_s": t_solve,
+            "newton_steps": st.total_newton, "krylov_iterations": st.total_krylov, "outer_steps": len(st.history["newton_steps"]),
+            "dofs_per_sec": s["num_rows"] * st.total_newton / t_solve, "history": st.history,
+            "device_bytes": s["device_bytes"], "max_memory_allocated_torch": torch.cuda.max_memory_allocated(),
+            "free_total_bytes": list(torch.cuda.mem_get_info()),
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
