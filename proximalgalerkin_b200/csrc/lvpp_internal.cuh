@@ -198,6 +198,7 @@ struct lvpp_problem {
   double mg_margin = 1.10;        // safety factor on the power-iteration estimate of lambda_max(Binv J)
   int mg_power_its = 10;
   int mg_power_boost = 1;         // multiplier of the power iterations (10 while re-estimating after a failed solve)
+  int32_t mg_best_its = 0;        // fewest Krylov iterations of a converged solve on this handle (adaptive Chebyshev ratio)
   int64_t mg_retries = 0;         // Krylov solves repeated after a re-estimate
   int mg_unroll = 4;              // slots per register buffer of k_packed_op (4 or 8)
   double mg_cheb = 10.0;          // > 1: Chebyshev-root damping of the sweeps over [b / mg_cheb, b]; else plain damping

@@ -811,14 +811,15 @@ static int estimate_lambda(lvpp_problem* h, MgLevel& L) {
   return 0;
 }
 
-// after a failed Krylov solve: forget the eigenvalue estimates and redo them from the fixed start vector with ten
-// times the iterations (krylov.cu retries the solve once)
+// after a failed Krylov solve: forget the eigenvalue estimates, redo them from the fixed start vector with ten
+// times the iterations and fall back to plain damping (krylov.cu retries the solve once)
 int lvpp_mg_reestimate(lvpp_problem* h) {
   for (MgLevel& L : h->levels) {
     L.ev_valid = false;
     L.lambda = 0.0;
   }
   h->mg_alpha_est = -1.0;
+  h->mg_cheb = 0.0;  // the retry (and the rest of this handle's life) uses plain damping: robust to eigenvalues off the interval
   h->mg_power_boost = 10;
   const int r = lvpp_mg_update(h);
   h->mg_power_boost = 1;
@@ -845,18 +846,18 @@ int lvpp_mg_update(lvpp_problem* h) {
     }
   // lambda_max(Binv J) is set by the stiffness block (mesh and element, much less by psi), so it is estimated when
   // alpha changes (once per proximal step), with a margin for the estimate's deficit and its drift over the Newton
-  // steps.
+  // steps.  The dampings are recomputed from it at every update (the Chebyshev ratio may have been adapted by
+  // lvpp_solve_linear in between).
   const bool estimate = !(h->mg_alpha_est == h->alpha);
   for (int l = 0; l + 1 < nl; ++l) {
     MgLevel& L = h->levels[l];
     CKR(build_binv(h, L));
-    if (!estimate) continue;
-    CKR(estimate_lambda(h, L));
+    if (estimate) CKR(estimate_lambda(h, L));
     // sweep k of a smoothing step is damped by omega_k.  Plain damped Jacobi: omega_k = omega.  Chebyshev
     // (mg_cheb = ratio > 1): 1 / omega_k are the roots of the degree-nsmooth Chebyshev polynomial of the
     // interval [b / ratio, b], b = margin * lambda_max -- the sweeps are the same kernel at the same cost, their
     // product is the polynomial that is smallest on the upper part of the spectrum.  An eigenvalue above b is
-    // amplified, which is why the estimate is warm-started and carries a margin.
+    // amplified, which is why the estimate is monotone, warm-started and carries a margin.
     L.omega = h->mg_omega * std::min(1.0, 2.0 / (h->mg_margin * L.lambda));
     for (int side = 0; side < 2; ++side) {  // pre- and post-smoothing polynomials may have different degrees
       const int m = side == 0 ? h->mg_npre : h->mg_npost;
