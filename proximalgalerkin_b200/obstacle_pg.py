@@ -131,13 +131,23 @@ class LvppStepper:
         self.total_krylov = 0
         self.finished = False
         self.history = {k: [] for k in ("newton_steps", "alpha", "primal_increment", "reason")}
+        self.nb, self.last_lambda = None, 1.0
+        if self.opts.snes_linesearch != 0:
+            from . import linesearch
+
+            o = self.opts
+            self.nb = linesearch.NewtonBT(linesearch.DeviceBackend(dev, o), rtol=o.snes_rtol, atol=o.snes_atol,
+                                          stol=o.snes_stol, max_it=o.snes_max_it, divtol=o.snes_divtol)
         self._begin_outer()
 
     def _begin_outer(self):
         self.alpha_value, self.alpha_k = alpha_update(self.alpha_scheme, self.k, self.alpha_value, self.alpha_k, self.alpha_max)
         self.dev.set_alpha(self.alpha_value)
         self.dev.set_previous(self.xk)
-        self.fnorm0 = self.dev.newton_begin(self.x)
+        if self.nb is not None:  # snes_linesearch_type bt: host loop over the library's entry points
+            self.fnorm0 = self.nb.begin(self.x)
+        else:
+            self.fnorm0 = self.dev.newton_begin(self.x)
         self.ttol = self.fnorm0 * self.opts.snes_rtol
         self.newton_its = 0
 
@@ -161,13 +171,21 @@ class LvppStepper:
         outer iteration (observables, stopping test, sol_k <- sol, alpha update) when SNES converges."""
         if self.finished:
             return False
-        (fnorm, ynorm, xnorm), kits, kreason = self.dev.newton_step(self.x, self.opts)
-        self.newton_its += 1
-        self.total_newton += 1
-        self.total_krylov += kits
-        reason = -3 if kreason < 0 else self._snes_reason(self.newton_its, xnorm, ynorm, fnorm)
-        if reason == 0 and self.newton_its >= self.opts.snes_max_it:
-            reason = -5
+        if self.nb is not None:
+            lin0 = self.nb.linear_its
+            reason = self.nb.step(self.x)
+            self.last_lambda = self.nb.last_lambda
+            self.newton_its = self.nb.its
+            self.total_newton += 1
+            self.total_krylov += self.nb.linear_its - lin0
+        else:
+            (fnorm, ynorm, xnorm), kits, kreason = self.dev.newton_step(self.x, self.opts)
+            self.newton_its += 1
+            self.total_newton += 1
+            self.total_krylov += kits
+            reason = -3 if kreason < 0 else self._snes_reason(self.newton_its, xnorm, ynorm, fnorm)
+            if reason == 0 and self.newton_its >= self.opts.snes_max_it:
+                reason = -5
         if reason == 0:
             return True
         if reason < 0:

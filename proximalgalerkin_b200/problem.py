@@ -347,7 +347,9 @@ def newton_options(options, generic=False):
     ls = opts.get("snes_linesearch_type", "bt" if generic else "none")
     if ls in ("none", "basic"):
         o.snes_linesearch = _capi.LINESEARCH_NONE
-    elif ls == "bt" and generic:
+    elif ls == "bt":
+        # mixed-form engine: inside the library (forms.cu); obstacle engine: the host loop of linesearch.py over
+        # the library's assembly / Krylov / J*v entry points
         o.snes_linesearch = _capi.LINESEARCH_BT
     else:
         raise NotImplementedError(f"snes_linesearch_type {ls!r}")
@@ -473,7 +475,19 @@ class SNESSolver:
         dev = self.problem.device_problem
         dev.sync_coefficients()
         xh = self.problem.u.x.array
-        reason, its, fnorm, lin = dev.newton_solve_host(xh, self._opts)  # writes xh only if reason > 0
+        if self._opts.snes_linesearch == _capi.LINESEARCH_BT:
+            from . import linesearch
+
+            o = self._opts
+            dev.x.set(xh)
+            nb = linesearch.NewtonBT(linesearch.DeviceBackend(dev, o), rtol=o.snes_rtol, atol=o.snes_atol, stol=o.snes_stol,
+                                     max_it=o.snes_max_it, divtol=o.snes_divtol)
+            reason, its = nb.solve(dev.x)
+            fnorm, lin = nb.fnorm, nb.linear_its
+            if reason > 0:  # SNESSolver.solve only overwrites the caller's function on convergence (problem.py:121-123)
+                xh[:] = dev.x.numpy()
+        else:
+            reason, its, fnorm, lin = dev.newton_solve_host(xh, self._opts)  # writes xh only if reason > 0
         self.converged_reason, self.iterations, self.fnorm, self.linear_iterations = reason, its, fnorm, lin
         if _flag(self.options, "snes_monitor"):
             print(f"  SNES: {its} Newton steps, ||F|| = {fnorm:.6e}, {lin} Krylov iterations, reason {reason}")

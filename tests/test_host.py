@@ -103,7 +103,9 @@ def test_option_parsing():
     assert lvpp.newton_options({"ksp_type": "gmres"}).pc_type == lvpp._capi.PC_MG
     assert lvpp.newton_options({"ksp_type": "gmres", "pc_type": "mg", "pc_mg_smoothing_sweeps": 3}).pc_degree == 3
     assert lvpp.newton_options({"ksp_type": "minres", "pc_type": "jacobi"}).pc_type == lvpp._capi.PC_JACOBI
-    for bad in ({"snes_linesearch_type": "bt"}, {"ksp_type": "gmres", "pc_type": "jacobi"}, {"ksp_type": "cg"},
+    assert lvpp.newton_options({"snes_linesearch_type": "bt"}).snes_linesearch == lvpp._capi.LINESEARCH_BT
+    assert lvpp.newton_options({"snes_linesearch_type": "none"}).snes_linesearch == lvpp._capi.LINESEARCH_NONE
+    for bad in ({"snes_linesearch_type": "cp"}, {"ksp_type": "gmres", "pc_type": "jacobi"}, {"ksp_type": "cg"},
                 {"pc_type": "hypre"}, {"snes_type": "vinewtonssls"}):
         with pytest.raises(NotImplementedError):
             lvpp.newton_options(bad)

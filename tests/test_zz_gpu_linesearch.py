@@ -1,0 +1,56 @@
+"""snes_linesearch_type bt on the obstacle engine (host loop of proximalgalerkin_b200/linesearch.py over the
+library's assembly / Krylov / J*v entry points) against the oracle's restated PETSc loop."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_obstacle_bt_matches_oracle(lib):
+    import proximalgalerkin_b200 as lvpp
+    from oracle import mesh as omesh
+    from oracle import obstacle as oobs
+    from oracle import snes as osnes
+    from proximalgalerkin_b200 import linesearch as ls
+
+    n, alpha = 6, 3.0
+    msh = lvpp.mesh.create_box(n, n, n)
+    s = lvpp.obstacle_pg.setup(msh, 1, petsc_options={"ksp_type": "gmres", "pc_type": "mg", "snes_linesearch_type": "bt"})
+    dev = s["problem"].device_problem
+    orc = oobs.ObstacleOracle(omesh.box_kuhn(n, n, n))
+    rng = np.random.default_rng(2)
+    xk = 0.3 * rng.standard_normal(orc.num_rows)
+    x0 = np.zeros(orc.num_rows)
+    x0[1::2] = -4.0  # the full Newton step overshoots from here: bt has to backtrack
+    xo, reason_o, its_o, hist_o = osnes.newton_ls(lambda z: orc.assemble_residual(z, xk, alpha), lambda z: orc.jacobian(z, alpha),
+                                                  x0, linesearch="bt", rtol=1e-10, max_it=60)
+    dev.set_alpha(alpha)
+    dev.set_previous(xk)
+    X = lvpp.DeviceVector(dev.n, dev.device)
+    X.set(x0)
+    opts = lvpp.newton_options(s["options"])
+    nb = ls.NewtonBT(ls.DeviceBackend(dev, opts), rtol=1e-10, max_it=60)
+    hist, lams = [nb.begin(X)], []
+    while not nb.reason:
+        nb.step(X)
+        hist.append(nb.fnorm)
+        lams.append(nb.last_lambda)
+    assert (nb.reason, nb.its) == (reason_o, its_o), (nb.reason, nb.its, reason_o, its_o)
+    assert min(lams) < 1.0
+    assert np.allclose(hist[: len(hist_o)], hist_o, rtol=1e-6, atol=1e-14)
+    assert np.linalg.norm(X.numpy() - xo) <= 1e-8 * np.linalg.norm(xo)
+
+
+def test_nonlinear_problem_bt_option(lib):
+    """The option routes NonlinearProblem.solve() through the same loop; from the zero start of the LVPP iteration
+    the full step is always accepted, so bt reproduces the line-search-free Newton counts."""
+    import proximalgalerkin_b200 as lvpp
+
+    msh = lvpp.mesh.create_rectangle(10, 10)
+    base = {"ksp_type": "gmres", "pc_type": "mg"}
+    _, tot_none, h_none = lvpp.obstacle_pg.solve_problem(msh, 1, 500, "double_exponential", 1e2, 1e-4, petsc_options=base)
+    _, tot_bt, h_bt = lvpp.obstacle_pg.solve_problem(msh, 1, 500, "double_exponential", 1e2, 1e-4,
+                                                     petsc_options=dict(base, snes_linesearch_type="bt"))
+    assert h_bt["reason"] == h_none["reason"]
+    assert h_bt["newton_steps"] == h_none["newton_steps"]
+    assert np.allclose(h_bt["primal_increment"], h_none["primal_increment"], rtol=1e-6)

@@ -19,6 +19,8 @@ def main():
     ap.add_argument("--size", type=int, default=215)
     ap.add_argument("--pc", default="mg")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--linesearch", default="none", choices=["none", "bt"],
+                    help="bt: PETSc's backtracking line search (the full step overshoots on fine 3-D meshes)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -34,11 +36,22 @@ def main():
     t0 = time.perf_counter()
     msh = lvpp.mesh.create_box(n, n, nz, rank=rank, nranks=world)
     opts = {"ksp_rtol": 1e-12, "ksp_type": "gmres", "pc_type": "mg"} if args.pc == "mg" else {"ksp_rtol": 1e-12}
+    opts["snes_linesearch_type"] = args.linesearch
     st = lvpp.obstacle_pg.LvppStepper(msh, 1, "double_exponential", 1e2, 1e-4, petsc_options=opts)
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t0
     t1 = time.perf_counter()
-    if args.verbose and rank == 0:  # log every Newton step: norms, Krylov iterations and reason
+    if args.verbose and rank == 0 and st.nb is not None:
+        inner_bt = st.nb.step
+
+        def logged_bt(x):
+            r = inner_bt(x)
+            print(f"outer {st.k} alpha {st.alpha_value:.4g} newton {st.nb.its}: |F| {st.nb.fnorm:.3e} lambda {st.nb.last_lambda:.3g} "
+                  f"krylov {st.nb.linear_its} reason {r}", file=sys.stderr, flush=True)
+            return r
+
+        st.nb.step = logged_bt
+    elif args.verbose and rank == 0:  # log every Newton step: norms, Krylov iterations and reason
         inner = st.dev.newton_step
 
         def logged(x, opts):
