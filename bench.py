@@ -161,6 +161,16 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def weak_scaling_mesh(n, world, weak="refine", slabs_1gpu=1):
+    """Cubes per axis and box of the N-GPU workload: (nxy, nz, lo, hi, slabs).  See the comment in run_b200."""
+    slabs = max(1, slabs_1gpu) if world == 1 else (world if weak == "stack" else 1)
+    if world > 1 and weak == "refine":
+        nxy = int(round(n * world ** (1.0 / 3.0)))
+        nz = world * max(2, int(round(nxy / world)))
+        return nxy, nz, (-1.0, -1.0, -1.0), (1.0, 1.0, 1.0), slabs
+    return n, n * slabs, (-1.0, -1.0, -float(slabs)), (1.0, 1.0, float(slabs)), slabs
+
+
 # ------------------------------------------------------------------------------------------------
 def run_b200(args):
     import numpy as np
@@ -185,14 +195,7 @@ def run_b200(args):
     # into N z-slabs.  "stack": N copies of the n^3 problem stacked along z on [-1,1]^2 x [-N,N] with one obstacle
     # per slab (the far slabs of a single obstacle see phi = -16 and the first Newton step from psi = 0 overshoots
     # past PETSc's divergence tolerance).  --slabs S emulates the S-GPU "stack" problem on one GPU (diagnostic).
-    slabs = max(1, args.slabs) if world == 1 else (world if args.weak == "stack" else 1)
-    if world > 1 and args.weak == "refine":
-        nxy = int(round(n * world ** (1.0 / 3.0)))
-        nz = world * max(2, int(round(nxy / world)))
-        lo, hi = (-1.0, -1.0, -1.0), (1.0, 1.0, 1.0)
-    else:
-        nxy, nz = n, n * slabs
-        lo, hi = (-1.0, -1.0, -float(slabs)), (1.0, 1.0, float(slabs))
+    nxy, nz, lo, hi, slabs = weak_scaling_mesh(n, world, args.weak, args.slabs)
     msh = lvpp.mesh.create_box(nxy, nxy, nz, lo=lo, hi=hi, rank=rank, nranks=world)
     opts = {"ksp_rtol": args.ksp_rtol, "ksp_max_it": 200000}
     if args.pc == "mg":

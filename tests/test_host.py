@@ -124,3 +124,18 @@ def test_no_cpu_fallback_and_no_oracle_in_product():
         s = lvpp.obstacle_pg.setup(msh)
         with pytest.raises(lvpp._capi.LvppError):
             s["problem"].solve()
+
+
+def test_bench_weak_scaling_mesh():
+    """bench.py's N-GPU workload: the refined one-obstacle cube keeps ~n^3 cubes per GPU and nz divisible by N."""
+    import bench
+
+    assert bench.weak_scaling_mesh(215, 1) == (215, 215, (-1.0, -1.0, -1.0), (1.0, 1.0, 1.0), 1)
+    for world, expect in ((2, (271, 272)), (4, (341, 340)), (8, (430, 432))):
+        nxy, nz, lo, hi, slabs = bench.weak_scaling_mesh(215, world)
+        assert (nxy, nz) == expect and nz % world == 0 and slabs == 1
+        assert (lo, hi) == ((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0))
+        per_gpu = nxy * nxy * nz / world
+        assert abs(per_gpu / 215**3 - 1.0) < 0.01
+    assert bench.weak_scaling_mesh(215, 8, "stack") == (215, 1720, (-1.0, -1.0, -8.0), (1.0, 1.0, 8.0), 8)
+    assert bench.weak_scaling_mesh(215, 1, "refine", 2) == (215, 430, (-1.0, -1.0, -2.0), (1.0, 1.0, 2.0), 2)
