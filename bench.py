@@ -346,6 +346,15 @@ def run_b200(args):
                "sample": f"{ns} Newton steps of the same LVPP solve on a {args.n_cpu}^3-cube Kuhn mesh ({rows_c} rows), "
                          f"numpy assembly + SuperLU (oracle/; sequential factorisation, threaded BLAS), {secs_c:.1f} s; "
                          f"host has {os.cpu_count()} cores"}
+        if not args.no_aux:
+            # like-for-like kernels on all host threads: the C + OpenMP restatement of SNESProblem.J and MatMult on the
+            # reference's monolithic CSR (GPU counterparts: `assembly` and `roofline_jv` of this line)
+            try:
+                from oracle import cpu_kernels
+
+                cpu["kernels"] = cpu_kernels.time_kernels(40)
+            except Exception as e:  # the baseline library is optional infrastructure
+                cpu["kernels"] = {"unavailable": str(e)[:200]}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": done, "warmup": args.warmup,

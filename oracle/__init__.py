@@ -16,6 +16,10 @@ tests, sparse LU) and anchors on the reference's own call sites:
 What *is* pinned: the alpha-schedule known answers, the obstacle closed form, exact P1 element
 matrices and the structural identities listed in SURVEY.md section 8c (tests/test_oracle_*.py).
 
+``oracle/c/lvpp_cpu.c`` (bound by ``oracle/cpu_kernels.py``) is the compiled part: the Jacobian assembly
+and MatMult of the reference on its own data layout in C + OpenMP, checked against the numpy functions
+here, used only as the all-cores CPU baseline of bench.py.
+
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this package.  The product (proximalgalerkin_b200) never does.
 """
