@@ -237,15 +237,18 @@ int lvpp_solve_linear(lvpp_problem* h, const double* d_rhs, double* d_y, const l
       CKR(lvpp_gmres_mg(h, d_rhs, d_y, o, &its2, &reason1, rnorm));
       its1 += its2;
     }
-    // The Chebyshev dampings are tuned for a real spectrum in (0, b].  Late in an LVPP solve exp(psi) -> 0 on the
-    // contact set, eigenvalues of Binv J leave that interval and the sharper polynomial amplifies them: at n = 215
-    // the solves of the second proximal step take 49 - 60 iterations with ratio 10 against 38 - 39 with plain
-    // damping (26 - 30 against 32 - 35 in the first).  So the ratio is halved whenever a solve needs 1.5 times the
-    // best count seen on this handle, down to plain damping.  Deterministic; identical on every rank.
-    if (h->mg_cheb > 1.0 && reason1 > 0 && its1 >= 8) {  // (a solve that converges at once says nothing)
+    // The Chebyshev dampings are built for a real spectrum in (0, b].  As the contact set develops (exp(psi) -> 0 on
+    // it) Binv J acquires complex eigenvalues (tools/mg_prototype.py --spectrum: none at the first Newton step, 250 of
+    // 1458 with |Im| up to 0.66 three proximal steps later on an 8^3 mesh; lambda_max stays 2.50 throughout) and a wide
+    // interval amplifies them: at n = 215 the solves of the second proximal step take 49 - 60 iterations with ratio 10
+    // against 26 - 30 in the first.  A narrow interval is robust -- on the prototype's 16^3 mesh ratio 4 stays at
+    // 16 - 28 iterations over four proximal steps while ratio 8 reaches 56 and plain damping 97 -- but costs 10 - 20 %
+    // in the first proximal step.  So the ratio starts at its default and is halved, down to 4, whenever a solve
+    // needs 1.5 times the best count seen on this handle.  Deterministic; identical on every rank.
+    if (h->mg_cheb > 4.0 && reason1 > 0 && its1 >= 8) {  // (a solve that converges at once says nothing)
       if (h->mg_best_its == 0 || its1 < h->mg_best_its) h->mg_best_its = its1;
       else if (2 * its1 > 3 * h->mg_best_its && its1 > h->mg_best_its + 8) {
-        h->mg_cheb = h->mg_cheb >= 4.0 ? 0.5 * h->mg_cheb : 0.0;
+        h->mg_cheb = std::max(4.0, 0.5 * h->mg_cheb);
         if (getenv("LVPP_MG_VERBOSE") && h->rank == 0)
           fprintf(stderr, "[lvpp mg] %d Krylov iterations (best %d): Chebyshev ratio -> %.3g\n", (int)its1, (int)h->mg_best_its, h->mg_cheb);
       }
