@@ -58,3 +58,38 @@ def test_nonlinear_problem_bt_option(lib):
     assert h_bt["reason"] == h_none["reason"]
     assert h_bt["newton_steps"] == h_none["newton_steps"]
     assert np.allclose(h_bt["primal_increment"], h_none["primal_increment"], rtol=1e-6)
+
+
+def test_residual_and_jacobian_at_extreme_latent_values(lib):
+    """States of a late proximal step: psi between -60 (deep inside the contact set) and +1 next to each other, u of
+    order 1e-2.  F and J against the oracle to the same 1e-12 as at the moderate states of tests/test_gpu_parity.py."""
+    import proximalgalerkin_b200 as lvpp
+    from oracle import mesh as omesh
+    from oracle import obstacle as oobs
+
+    n = 8
+    msh = lvpp.mesh.create_box(n, n, n)
+    s = lvpp.obstacle_pg.setup(msh, 1)
+    dev = s["problem"].device_problem
+    orc = oobs.ObstacleOracle(omesh.box_kuhn(n, n, n))
+    rng = np.random.default_rng(9)
+    x = np.zeros(orc.num_rows)
+    x[0::2] = 1e-2 * rng.standard_normal(orc.num_rows // 2)
+    x[1::2] = np.where(rng.random(orc.num_rows // 2) > 0.5, -60.0 + 30.0 * rng.random(orc.num_rows // 2), rng.random(orc.num_rows // 2))
+    xk = x.copy()
+    xk[1::2] += 20.0 * rng.random(orc.num_rows // 2)
+    alpha = 1.49
+    dev.set_alpha(alpha)
+    dev.set_previous(xk)
+    X, F = lvpp.DeviceVector(dev.n, dev.device), lvpp.DeviceVector(dev.n, dev.device)
+    X.set(x)
+    dev.assemble_residual(X, F)
+    Fo = orc.assemble_residual(x, xk, alpha)
+    assert np.abs(F.numpy() - Fo).max() <= 1e-12 * np.abs(Fo).max()
+    vals = dev.jacobian_values().cpu().numpy()
+    vo = orc.assemble_jacobian_values(x, alpha)
+    assert np.abs(vals - vo).max() <= 1e-12 * np.abs(vo).max()
+    # entries of D span 26 orders of magnitude: compare them relative to themselves as well, where they are not
+    # below the rounding level of the sums they sit in
+    big = np.abs(vo) > 1e-14 * np.abs(vo).max()
+    assert np.abs(vals[big] - vo[big]).max() <= 1e-9 * np.abs(vo[big]).max()
