@@ -241,10 +241,11 @@ int lvpp_solve_linear(lvpp_problem* h, const double* d_rhs, double* d_y, const l
     // it) Binv J acquires complex eigenvalues (tools/mg_prototype.py --spectrum: none at the first Newton step, 250 of
     // 1458 with |Im| up to 0.66 three proximal steps later on an 8^3 mesh; lambda_max stays 2.50 throughout) and a wide
     // interval amplifies them: at n = 215 the solves of the second proximal step take 49 - 60 iterations with ratio 10
-    // against 26 - 30 in the first.  A narrow interval is robust -- on the prototype's 16^3 mesh ratio 4 stays at
-    // 16 - 28 iterations over four proximal steps while ratio 8 reaches 56 and plain damping 97 -- but costs 10 - 20 %
-    // in the first proximal step.  So the ratio starts at its default and is halved, down to 4, whenever a solve
-    // needs 1.5 times the best count seen on this handle.  Deterministic; identical on every rank.
+    // against 26 - 30 in the first; on the prototype's 16^3 mesh ratio 10 goes from 15 - 20 to 52 - 65 over four
+    // proximal steps while ratio 6 stays at 15 - 24, ratio 4 at 16 - 23 and plain damping at 17 - 23.  The default
+    // ratio is therefore 6 (3 % more iterations than 10 in the first proximal step at n = 215), and as a safety net
+    // the ratio is halved, down to 4, whenever a solve needs 1.5 times the best count seen on this handle.
+    // Deterministic; identical on every rank.
     if (h->mg_cheb > 4.0 && reason1 > 0 && its1 >= 8) {  // (a solve that converges at once says nothing)
       if (h->mg_best_its == 0 || its1 < h->mg_best_its) h->mg_best_its = its1;
       else if (2 * its1 > 3 * h->mg_best_its && its1 > h->mg_best_its + 8) {

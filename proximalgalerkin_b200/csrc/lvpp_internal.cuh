@@ -201,7 +201,7 @@ struct lvpp_problem {
   int32_t mg_best_its = 0;        // fewest Krylov iterations of a converged solve on this handle (adaptive Chebyshev ratio)
   int64_t mg_retries = 0;         // Krylov solves repeated after a re-estimate
   int mg_unroll = 4;              // slots per register buffer of k_packed_op (4 or 8)
-  double mg_cheb = 10.0;          // > 1: Chebyshev-root damping of the sweeps over [b / mg_cheb, b]; else plain damping
+  double mg_cheb = 6.0;           // > 1: Chebyshev-root damping of the sweeps over [b / mg_cheb, b]; else plain damping
   double mg_alpha_est = -1.0;     // alpha of the last smoother eigenvalue estimate
   double* coarse_lu = nullptr;    // dense inverse of the coarsest operator (all ranks' rows) [nc * nc]
   int coarse_n = 0;               // global unknowns of the coarsest level

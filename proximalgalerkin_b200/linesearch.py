@@ -6,8 +6,8 @@ switch the line search on where the full Newton step is not robust (``bt``:
 examples/05_thermoforming/thermoforming_dolfinx.py:99-111, the PETSc default used by
 examples/04_multiphase/multiphase_dolfinx.py:128-143) -- and the full step stops being
 robust for the 3-D obstacle problem on fine meshes: the largest increase of psi in the first Newton step
-of a proximal iteration grows with the resolution (0.05, 2.8, 5.8, 7.2 for n = 8, 12, 16, 20 cubes per
-axis at alpha = 1.49) and at n = 215 the exponential overshoots (||F|| jumps from 5e-3 to 0.23, then to
+of a proximal iteration depends on how the mesh meets the contact boundary (0.05, 2.8, 5.8, 7.2, 0.9 for
+n = 8, 12, 16, 20, 24 cubes per axis at alpha = 1.49) and at n = 215 the exponential overshoots (||F|| jumps from 5e-3 to 0.23, then to
 3e28).  With ``snes_linesearch_type bt`` the same Newton direction is damped until
 0.5 ||F||^2 decreases sufficiently.
 

@@ -132,10 +132,17 @@ class Multigrid:
             v = w
         return lam
 
-    def set_smoother(self, cheb=10.0, margin=1.10, npre=2, npost=2, exact_lambda=False):
+    LAMBDA_HISTORY = {}  # level index -> largest estimate so far (the library's estimate is monotone per handle)
+
+    def set_smoother(self, cheb=10.0, margin=1.10, npre=2, npost=2, exact_lambda=False, monotone=True):
         self.npre, self.npost = npre, npost
-        for L in self.levels[:-1]:
-            lam = self.lambda_max(L, exact=exact_lambda)
+        for li, L in enumerate(self.levels[:-1]):
+            if not hasattr(L, "lam_raw"):
+                L.lam_raw = self.lambda_max(L, exact=exact_lambda)
+            lam = L.lam_raw
+            if monotone:
+                lam = max(lam, Multigrid.LAMBDA_HISTORY.get(li, 0.0))
+                Multigrid.LAMBDA_HISTORY[li] = lam
             L.lam = lam
 
             def roots(m):
@@ -269,6 +276,8 @@ def main():
         L0 = mg.levels[0]
         rhs = to_blocked(orc, F)
         line = f"outer {k} alpha {alpha:.3g} newton {it}: levels {[L.N for L in mg.levels]}"
+        mg.set_smoother()
+        line += f" lam0 {mg.levels[0].lam_raw:.2f}->{mg.levels[0].lam:.2f}"
         if args.spectrum:
             A = (L0.Binv @ L0.J).toarray() if L0.N <= 1500 else None
             if A is not None:
