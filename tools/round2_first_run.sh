@@ -1,0 +1,14 @@
+#!/bin/bash
+# First GPU call of the next round (one B200, about 4 minutes): everything that was changed after the last GPU
+# minute of round 1, then the open question of DESIGN.md 7a.
+#   gpurun --timeout 900 -- tools/round2_first_run.sh
+mkdir -p gpurun_out
+(timeout 400 python -m pytest tests -m gpu -q -rxX 2>&1 | tail -15) | tee gpurun_out/r2_tests.txt
+python bench.py > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err; tail -1 gpurun_out/r2_bench.json | cut -c1-300
+for cfg in "--linesearch none" "--linesearch bt" "--linesearch none --snes-rtol 1e-9" "--linesearch bt --snes-rtol 1e-9"; do
+  tag=$(echo "$cfg" | tr -d ' -' )
+  echo "== full solve n=215 $cfg"
+  LVPP_MG_VERBOSE=1 timeout 200 python tools/full_solve.py --size 215 --verbose $cfg > gpurun_out/r2_full215_$tag.json 2> gpurun_out/r2_full215_$tag.err
+  grep -E "^outer|Chebyshev ratio|retrying|Error" gpurun_out/r2_full215_$tag.err | tail -40
+  tail -1 gpurun_out/r2_full215_$tag.json | cut -c1-600
+done
