@@ -641,6 +641,7 @@ int lvpp_mg_setup(lvpp_problem* h) {
   h->mg_margin = env_double("LVPP_MG_MARGIN", h->mg_margin);
   h->mg_power_its = (int)env_double("LVPP_MG_POWER_ITS", h->mg_power_its);
   h->gm_eta2 = env_double("LVPP_GMRES_ETA2", h->gm_eta2);
+  h->gm_fused_norm = env_double("LVPP_GMRES_FUSED_NORM", 0.0) != 0.0;
   // GMRES workspace (also the scratch of the collective decisions below)
   h->gm_restart = (int)env_double("LVPP_GMRES_RESTART", 50);
   if (h->gm_restart < 2 || h->gm_restart > 200) { lvpp_set_error("bad LVPP_GMRES_RESTART"); return LVPP_E_INVALID; }
@@ -1031,19 +1032,32 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
       for (int k = 0; k <= j + 1; ++k) hcol[k] = 0.0;
       double beta = 0.0;
       for (int pass = 0; pass < 2; ++pass) {
-        for (int k0 = 0; k0 <= j; k0 += GM_CHUNK) {
-          const int nv = std::min(GM_CHUNK, j + 1 - k0);
+        // LVPP_GMRES_FUSED_NORM=1 (experimental, off by default): the first pass also takes w . w (w is basis slot
+        // j + 1), so that beta^2 = ||w||^2 - sum h_k^2 needs no second reduction / host synchronisation; the explicit
+        // norm is only fetched when the re-orthogonalisation test fails (then beta^2 is a small difference)
+        const bool fused = h->gm_fused_norm && pass == 0;
+        const int ndots = fused ? j + 2 : j + 1;
+        for (int k0 = 0; k0 < ndots; k0 += GM_CHUNK) {
+          const int nv = std::min(GM_CHUNK, ndots - k0);
           LAUNCH(h, k_multi_dot, nb, 256, 0, Vown, Vb, stride2, k0, nv, (const double2*)vec(j + 1), nb, gpart);
         }
         CK(cudaGetLastError());
-        CKR(reduce_to_host(h, gpart, j + 1, h->gm_h, h->gm_h_host));
+        CKR(reduce_to_host(h, gpart, ndots, h->gm_h, h->gm_h_host));
         double hsq = 0.0;
         for (int k = 0; k <= j; ++k) { hcol[k] += h->gm_h_host[k]; hsq += h->gm_h_host[k] * h->gm_h_host[k]; }
+        const double ww = fused ? h->gm_h_host[j + 1] : 0.0;
         // coefficients are already on the device in gm_h (all-reduced)
         LAUNCH(h, k_gmres_update, nb, 256, 0, Vown, Vb, stride2, j + 1, h->gm_h, (double2*)vec(j + 1), nb, m + 1, gpart);
         CK(cudaGetLastError());
-        CKR(reduce_to_host(h, gpart + (size_t)(m + 1) * nb, 1, h->gm_h + m + 2, h->gm_h_host + m + 2));
-        beta = sqrt(h->gm_h_host[m + 2]);
+        bool have_beta = false;
+        if (fused && ww - hsq > h->gm_eta2 * ww) {
+          beta = sqrt(ww - hsq);
+          have_beta = true;
+        }
+        if (!have_beta) {
+          CKR(reduce_to_host(h, gpart + (size_t)(m + 1) * nb, 1, h->gm_h + m + 2, h->gm_h_host + m + 2));
+          beta = sqrt(h->gm_h_host[m + 2]);
+        }
         if (pass == 0) {
           float sms = 0.f;
           CK(cudaEventElapsedTime(&sms, h->evs0, h->evs1));
