@@ -166,7 +166,10 @@ def weak_scaling_mesh(n, world, weak="refine", slabs_1gpu=1):
     slabs = max(1, slabs_1gpu) if world == 1 else (world if weak == "stack" else 1)
     if world > 1 and weak == "refine":
         nxy = int(round(n * world ** (1.0 / 3.0)))
-        nz = world * max(2, int(round(nxy / world)))
+        # an even number of planes per rank: every rank aggregates from its own first plane, so an odd count leaves a
+        # one-plane layer of thin aggregates at every slab boundary already on the first coarsening
+        # (tools/mg_prototype.py --slabs: 16 -> 18 Krylov iterations with 6-7 planes per slab, 16 -> 16 with 8)
+        nz = 2 * world * max(1, int(round(nxy / (2.0 * world))))
         return nxy, nz, (-1.0, -1.0, -1.0), (1.0, 1.0, 1.0), slabs
     return n, n * slabs, (-1.0, -1.0, -float(slabs)), (1.0, 1.0, float(slabs)), slabs
 
@@ -191,7 +194,7 @@ def run_b200(args):
     n = args.n
     t_setup = time.perf_counter()
     # Weak scaling (N > 1).  "refine" (default): the reference's problem -- one obstacle on [-1,1]^3 -- on a mesh
-    # refined so that every GPU keeps ~n^3 cubes: nx = ny = round(n N^(1/3)), nz = the multiple of N nearest to nx, cut
+    # refined so that every GPU keeps ~n^3 cubes: nx = ny = round(n N^(1/3)), nz = the multiple of 2N nearest to nx, cut
     # into N z-slabs.  "stack": N copies of the n^3 problem stacked along z on [-1,1]^2 x [-N,N] with one obstacle
     # per slab (the far slabs of a single obstacle see phi = -16 and the first Newton step from psi = 0 overshoots
     # past PETSc's divergence tolerance).  --slabs S emulates the S-GPU "stack" problem on one GPU (diagnostic).

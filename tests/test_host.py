@@ -131,11 +131,11 @@ def test_bench_weak_scaling_mesh():
     import bench
 
     assert bench.weak_scaling_mesh(215, 1) == (215, 215, (-1.0, -1.0, -1.0), (1.0, 1.0, 1.0), 1)
-    for world, expect in ((2, (271, 272)), (4, (341, 340)), (8, (430, 432))):
+    for world, expect in ((2, (271, 272)), (4, (341, 344)), (8, (430, 432))):
         nxy, nz, lo, hi, slabs = bench.weak_scaling_mesh(215, world)
-        assert (nxy, nz) == expect and nz % world == 0 and slabs == 1
+        assert (nxy, nz) == expect and nz % (2 * world) == 0 and slabs == 1  # even number of planes per rank
         assert (lo, hi) == ((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0))
         per_gpu = nxy * nxy * nz / world
-        assert abs(per_gpu / 215**3 - 1.0) < 0.01
+        assert abs(per_gpu / 215**3 - 1.0) < 0.015
     assert bench.weak_scaling_mesh(215, 8, "stack") == (215, 1720, (-1.0, -1.0, -8.0), (1.0, 1.0, 8.0), 8)
     assert bench.weak_scaling_mesh(215, 1, "refine", 2) == (215, 430, (-1.0, -1.0, -2.0), (1.0, 1.0, 2.0), 2)

@@ -81,7 +81,7 @@ class Level:
 
 
 class Multigrid:
-    def __init__(self, orc, x, alpha, slabs=1, over=1.8, coarse_target=96, max_levels=12, smooth=0.0):
+    def __init__(self, orc, x, alpha, slabs=1, over=1.8, coarse_target=96, max_levels=12, smooth=0.0, slab_levels=99):
         K, M, D = scalar_blocks(orc, x)
         coords = orc.node_coords
         h0 = np.min(np.diff(np.unique(np.round(coords[:, 0], 12))))
@@ -101,6 +101,15 @@ class Multigrid:
             box[:, ax] -= first[slab]
         self.levels = [Level(K, M, D, bc, box, slab)]
         while self.levels[-1].N > coarse_target and len(self.levels) < max_levels:
+            if len(self.levels) - 1 == slab_levels and slabs > 1:
+                # the replicated part of the hierarchy: from here down aggregates ignore the rank
+                # boundaries; box coordinates go back to the global grid of this level
+                L = self.levels[-1]
+                shift = np.array([L.box[L.slab == s_, ax].max() + 1 for s_ in range(slabs)])
+                off = np.concatenate([[0], np.cumsum(shift)[:-1]])
+                L.box = L.box.copy()
+                L.box[:, ax] += off[L.slab]
+                L.slab = np.zeros_like(L.slab)
             c = self.levels[-1].coarsen(smooth)
             if c.N >= self.levels[-1].N:
                 self.levels[-1].P = None
@@ -263,6 +272,8 @@ def main():
     ap.add_argument("--slabs", type=int, default=1)
     ap.add_argument("--over", type=float, default=1.8)
     ap.add_argument("--spectrum", action="store_true")
+    ap.add_argument("--slab-levels", dest="slab_levels", type=int, default=99,
+                    help="confine aggregates to the slabs only for the first L coarsenings (the replicated hierarchy below)")
     ap.add_argument("--smooth", type=float, default=0.0, help="smoothed-aggregation damping (0 = plain aggregation)")
     ap.add_argument("--configs", default="plain,cheb10", help="comma list: plain, chebR, wplain, wchebR (w = W-cycle)")
     args = ap.parse_args()
@@ -272,7 +283,7 @@ def main():
     states = newton_states(orc, args.outer)
     print(f"# {args.dim}-D n={n}: {orc.num_rows} rows, {len(states)} Newton steps in {args.outer} proximal steps, slabs={args.slabs}")
     for (k, it, x, xk, alpha, F) in states:
-        mg = Multigrid(orc, x, alpha, slabs=args.slabs, over=args.over, smooth=args.smooth)
+        mg = Multigrid(orc, x, alpha, slabs=args.slabs, over=args.over, smooth=args.smooth, slab_levels=args.slab_levels)
         L0 = mg.levels[0]
         rhs = to_blocked(orc, F)
         line = f"outer {k} alpha {alpha:.3g} newton {it}: levels {[L.N for L in mg.levels]}"
