@@ -47,11 +47,25 @@ def tabulate_lagrange(degree, points):
     return phi, dphi
 
 
+def _host_zeros(n):
+    """Zeroed float64 host vector; page-locked when a CUDA device is present, so that the H2D / D2H copies of
+    ``sol`` and ``sol_k`` around every proximal step (``lvpp_newton_solve_host``, ``lvpp_set_previous_host``) run
+    at PCIe speed instead of through the driver's pageable-memory staging.  The numpy view keeps the tensor alive."""
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            return torch.zeros(n, dtype=torch.float64, pin_memory=True).numpy()
+    except Exception:
+        pass
+    return np.zeros(n, dtype=np.float64)
+
+
 class _Array:
     """``Function.x``: owns the host array (``.array``), like dolfinx.la.Vector."""
 
     def __init__(self, n):
-        self.array = np.zeros(n, dtype=np.float64)
+        self.array = _host_zeros(n)
 
     def scatter_forward(self):  # ghosts are refreshed on the device by the solver
         return None
