@@ -237,21 +237,20 @@ int lvpp_solve_linear(lvpp_problem* h, const double* d_rhs, double* d_y, const l
       CKR(lvpp_gmres_mg(h, d_rhs, d_y, o, &its2, &reason1, rnorm));
       its1 += its2;
     }
-    // The Chebyshev dampings are built for a real spectrum in (0, b].  As the contact set develops (exp(psi) -> 0 on
-    // it) Binv J acquires complex eigenvalues (tools/mg_prototype.py --spectrum: none at the first Newton step, 250 of
-    // 1458 with |Im| up to 0.66 three proximal steps later on an 8^3 mesh; lambda_max stays 2.50 throughout) and a wide
-    // interval amplifies them: at n = 215 the solves of the second proximal step take 49 - 60 iterations with ratio 10
-    // against 26 - 30 in the first; on the prototype's 16^3 mesh ratio 10 goes from 15 - 20 to 52 - 65 over four
-    // proximal steps while ratio 6 stays at 15 - 24, ratio 4 at 16 - 23 and plain damping at 17 - 23.  The default
-    // ratio is therefore 6 (3 % more iterations than 10 in the first proximal step at n = 215), and as a safety net
-    // the ratio is halved, down to 4, whenever a solve needs 1.5 times the best count seen on this handle.
-    // Deterministic; identical on every rank.
-    if (h->mg_cheb > 4.0 && reason1 > 0 && its1 >= 8) {  // (a solve that converges at once says nothing)
+    // The Chebyshev dampings pay in the first proximal step (26 - 30 Krylov iterations per Newton step at n = 215
+    // against 32 - 35 with plain damping) and lose later: once the contact set has developed (exp(psi) -> 0 on it)
+    // the solves of the second proximal step take 49 - 60 iterations with ratio 10 against 38 - 39 with plain damping,
+    // and on the hardest systems of a CPU emulation of the whole solve (tools/full_solve_cpu.py, 40^3 mesh, second
+    // Newton step at alpha = 5.3) plain damping needs 72 iterations where ratios 10 / 6 / 4 need 104 / 209 / > 300 --
+    // no ratio is uniformly safe there.  So: start with the default ratio and fall back to plain damping, for the
+    // rest of the handle's life, the first time a solve needs 1.5 times the best count seen.  Deterministic;
+    // identical on every rank.
+    if (h->mg_cheb > 1.0 && reason1 > 0 && its1 >= 8) {  // (a solve that converges at once says nothing)
       if (h->mg_best_its == 0 || its1 < h->mg_best_its) h->mg_best_its = its1;
       else if (2 * its1 > 3 * h->mg_best_its && its1 > h->mg_best_its + 8) {
-        h->mg_cheb = std::max(4.0, 0.5 * h->mg_cheb);
+        h->mg_cheb = 0.0;
         if (getenv("LVPP_MG_VERBOSE") && h->rank == 0)
-          fprintf(stderr, "[lvpp mg] %d Krylov iterations (best %d): Chebyshev ratio -> %.3g\n", (int)its1, (int)h->mg_best_its, h->mg_cheb);
+          fprintf(stderr, "[lvpp mg] %d Krylov iterations (best %d): plain damping from here on\n", (int)its1, (int)h->mg_best_its);
       }
     }
     if (its) *its = its1;
