@@ -916,7 +916,7 @@ static int form_gmres(lvpp_form_problem* h, const double* d_rhs, double* d_y, co
       LAUNCH(h, k_axpby, nb, 256, 0, n2, 1.0, (const double2*)d_rhs, 1, (double2*)vec(0));
       CK(cudaGetLastError());
     }
-    LAUNCH(h, k_multi_dot, nb, 256, 0, n2, Vb, stride2, 0, 1, (const double2*)vec(0), nb, gpart);
+    LAUNCH(h, k_multi_dot, nb, 256, 0, n2, Vb, stride2, 0, 1, (const double2*)vec(0), nb, gpart, 1.0);
     CK(cudaGetLastError());
     CKR(form_reduce(h, gpart, 1, hh.data()));
     rnorm = sqrt(hh[0]);
@@ -941,13 +941,13 @@ static int form_gmres(lvpp_form_problem* h, const double* d_rhs, double* d_y, co
       for (int pass = 0; pass < 2; ++pass) {
         for (int k0 = 0; k0 <= j; k0 += GM_CHUNK) {
           const int nv = std::min(GM_CHUNK, j + 1 - k0);
-          LAUNCH(h, k_multi_dot, nb, 256, 0, n2, Vb, stride2, k0, nv, (const double2*)vec(j + 1), nb, gpart);
+          LAUNCH(h, k_multi_dot, nb, 256, 0, n2, Vb, stride2, k0, nv, (const double2*)vec(j + 1), nb, gpart, 1.0);
         }
         CK(cudaGetLastError());
         LAUNCH(h, k_reduce_multi, (j + 1) < 64 ? (j + 1) : 64, 256, 0, nb, j + 1, gpart, hdev);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(hh.data(), hdev, sizeof(double) * (j + 1), cudaMemcpyDeviceToHost, h->stream));
-        LAUNCH(h, k_gmres_update, nb, 256, 0, n2, Vb, stride2, j + 1, hdev, (double2*)vec(j + 1), nb, m + 1, gpart);
+        LAUNCH(h, k_gmres_update, nb, 256, 0, n2, Vb, stride2, j + 1, hdev, (double2*)vec(j + 1), nb, m + 1, gpart, 1.0);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(h->stream));
         double hsq = 0.0;

@@ -8,16 +8,19 @@
 
 // ------------------------------------------------------------------------------------------------
 // GMRES kernels
-// partial sums of V_k . w for k = k0 .. k0+nv-1 (nv <= GM_CHUNK); partials[(k0 + k) * nparts + block]
+// partial sums of V_k . w for k = k0 .. k0+nv-1 (nv <= GM_CHUNK); partials[(k0 + k) * nparts + block].
+// wy weighs the second component of every pair (1 = Euclidean; the obstacle path's equilibrated residual norm
+// weighs the psi rows, multigrid.cu)
 static __global__ void __launch_bounds__(256)
 k_multi_dot(int64_t Vown, const double2* __restrict__ Vb, int64_t stride2, int k0, int nv,
-            const double2* __restrict__ w, int nparts, double* __restrict__ partials) {
+            const double2* __restrict__ w, int nparts, double* __restrict__ partials, double wy) {
   __shared__ double s_red[32];
   double acc[GM_CHUNK];
 #pragma unroll
   for (int k = 0; k < GM_CHUNK; ++k) acc[k] = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vown; i += (int64_t)gridDim.x * blockDim.x) {
-    const double2 wi = w[i];
+    double2 wi = w[i];
+    wi.y *= wy;
 #pragma unroll
     for (int k = 0; k < GM_CHUNK; ++k)
       if (k < nv) {
@@ -36,7 +39,7 @@ k_multi_dot(int64_t Vown, const double2* __restrict__ Vb, int64_t stride2, int k
 // w -= sum_k hc[k] V_k (k < nv); partial ||w_new||^2 into partials[slot * nparts + block]
 static __global__ void __launch_bounds__(256)
 k_gmres_update(int64_t Vown, const double2* __restrict__ Vb, int64_t stride2, int nv, const double* __restrict__ hc,
-               double2* __restrict__ w, int nparts, int slot, double* __restrict__ partials) {
+               double2* __restrict__ w, int nparts, int slot, double* __restrict__ partials, double wy) {
   __shared__ double s_red[32];
   double part = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vown; i += (int64_t)gridDim.x * blockDim.x) {
@@ -48,7 +51,7 @@ k_gmres_update(int64_t Vown, const double2* __restrict__ Vb, int64_t stride2, in
       wi.y -= c * v.y;
     }
     w[i] = wi;
-    part += wi.x * wi.x + wi.y * wi.y;
+    part += wi.x * wi.x + wy * (wi.y * wi.y);
   }
   const double r = lvpp_block_sum<256>(part, s_red);
   if (threadIdx.x == 0) partials[(int64_t)slot * nparts + blockIdx.x] = r;

@@ -212,6 +212,8 @@ struct lvpp_problem {
   int gm_restart = 0;
   // classical Gram-Schmidt is repeated when less than eta2 of ||w||^2 survives the projection (Daniel et al.)
   double gm_eta2 = 0.01;         // (0.5 = Daniel's criterion; PETSc's default never repeats; profiles/r01_mg_scan.txt)
+  bool gm_weight_auto = false;    // experimental: equilibrated residual norm (weight on the psi rows), multigrid.cu
+  double gm_weight = 1.0, gm_weight_alpha = -1.0;
   bool gm_fused_norm = false;     // experimental: ||w||^2 taken in the dot pass (one reduction per iteration)
   double* gm_h = nullptr;         // device [restart + 2]
   double* gm_h_host = nullptr;    // pinned

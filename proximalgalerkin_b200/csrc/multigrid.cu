@@ -642,6 +642,7 @@ int lvpp_mg_setup(lvpp_problem* h) {
   h->mg_power_its = (int)env_double("LVPP_MG_POWER_ITS", h->mg_power_its);
   h->gm_eta2 = env_double("LVPP_GMRES_ETA2", h->gm_eta2);
   h->gm_fused_norm = env_double("LVPP_GMRES_FUSED_NORM", 0.0) != 0.0;
+  if (const char* gw = getenv("LVPP_GMRES_WEIGHT")) h->gm_weight_auto = strcmp(gw, "auto") == 0;
   // GMRES workspace (also the scratch of the collective decisions below)
   h->gm_restart = (int)env_double("LVPP_GMRES_RESTART", 50);
   if (h->gm_restart < 2 || h->gm_restart > 200) { lvpp_set_error("bad LVPP_GMRES_RESTART"); return LVPP_E_INVALID; }
@@ -787,7 +788,7 @@ static int estimate_lambda(lvpp_problem* h, MgLevel& L) {
   double lam = 0.0;
   for (int it = 0; it <= nit; ++it) {
     // normalise ev, then t = ev + Binv J ev
-    LAUNCH(h, k_multi_dot, nb, 256, 0, L.Vown, (const double2*)L.ev, L.V, 0, 1, (const double2*)L.ev, nb, h->gm_part);
+    LAUNCH(h, k_multi_dot, nb, 256, 0, L.Vown, (const double2*)L.ev, L.V, 0, 1, (const double2*)L.ev, nb, h->gm_part, 1.0);
     CK(cudaGetLastError());
     CKR(reduce_to_host(h, h->gm_part, 1, h->gm_h, h->gm_h_host));
     const double nrm = sqrt(h->gm_h_host[0]);
@@ -967,6 +968,25 @@ int lvpp_mg_vcycle(lvpp_problem* h, const double* b_in, double** z_out) {
   return 0;
 }
 
+// partial sums of K_ii and M_ii over the owned free nodes: partials[0 * nparts + block], partials[1 * nparts + block]
+__global__ void __launch_bounds__(256) k_diag_sums(int64_t Vown, const int64_t* __restrict__ slice_ptr,
+                                                   const uint8_t* __restrict__ diag_k, const double* __restrict__ K,
+                                                   const double* __restrict__ M, const uint8_t* __restrict__ bc, int nparts,
+                                                   double* __restrict__ partials) {
+  __shared__ double s_red[32];
+  double sk = 0.0, sm = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vown; i += (int64_t)gridDim.x * blockDim.x) {
+    if (bc[i]) continue;
+    const int64_t idx = slice_ptr[i >> 5] + (i & 31) + (int64_t)diag_k[i] * LVPP_SLICE;
+    sk += K[idx];
+    sm += M[idx];
+  }
+  const double rk = lvpp_block_sum<256>(sk, s_red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = rk;
+  const double rm = lvpp_block_sum<256>(sm, s_red);
+  if (threadIdx.x == 0) partials[(int64_t)nparts + blockIdx.x] = rm;
+}
+
 // ------------------------------------------------------------------------------------------------
 // right-preconditioned restarted GMRES:  J M^-1 (M y) = rhs
 static int reduce_to_host(lvpp_problem* h, double* partials, int nvals, double* dst_dev, double* dst_host) {
@@ -993,6 +1013,24 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
   double bnorm = 0.0, rnorm = 0.0, tol = 0.0;
   bool first = true;
   MgLevel& L0 = h->levels[0];
+  // Equilibrated residual norm (LVPP_GMRES_WEIGHT=auto, experimental, off by default): the rows of the u equation
+  // carry entries of size alpha K_ii, those of the psi equation entries of size M_ii = O(h^2 / alpha) times that, and a
+  // Euclidean residual norm all but ignores the latter.  On the developed contact set this is what makes restarted
+  // GMRES stagnate (tools/full_solve_cpu.py: 72 - 300+ iterations on a 40^3 mesh at alpha = 5.3 against 28 with the
+  // weight; 600+ at 64^3).  With the weight wy = sum alpha K_ii / sum M_ii on the psi component of every inner product
+  // GMRES runs on S J S, S = diag(1, sqrt(wy)), without touching the operator or the cycle.
+  double wy = 1.0;
+  if (h->gm_weight_auto) {
+    if (!(h->gm_weight_alpha == h->alpha)) {
+      LAUNCH(h, k_diag_sums, nb, 256, 0, Vown, L0.slice_ptr, L0.diag_k, L0.K, L0.M, L0.bc_flag, nb, gpart);
+      CK(cudaGetLastError());
+      CKR(reduce_to_host(h, gpart, 2, h->gm_h, h->gm_h_host));
+      if (!(h->gm_h_host[0] > 0.0) || !(h->gm_h_host[1] > 0.0)) { lvpp_set_error("GMRES weight: bad diagonal sums"); return LVPP_E_INVALID; }
+      h->gm_weight = h->alpha * h->gm_h_host[0] / h->gm_h_host[1];
+      h->gm_weight_alpha = h->alpha;
+    }
+    wy = h->gm_weight;
+  }
   CK(cudaMemsetAsync(d_y, 0, sizeof(double) * 2 * h->V, h->stream));
   while (reason == 0) {
     // r = rhs - J y  (first cycle: y = 0)
@@ -1001,7 +1039,7 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
     } else {
       CKR(level_op(h, L0, EPI_RESID, 1.0, d_y, d_rhs, vec(0), false));
     }
-    LAUNCH(h, k_multi_dot, nb, 256, 0, Vown, Vb, stride2, 0, 1, (const double2*)vec(0), nb, gpart);
+    LAUNCH(h, k_multi_dot, nb, 256, 0, Vown, Vb, stride2, 0, 1, (const double2*)vec(0), nb, gpart, wy);
     CK(cudaGetLastError());
     CKR(reduce_to_host(h, gpart, 1, h->gm_h, h->gm_h_host));
     rnorm = sqrt(h->gm_h_host[0]);
@@ -1039,7 +1077,7 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
         const int ndots = fused ? j + 2 : j + 1;
         for (int k0 = 0; k0 < ndots; k0 += GM_CHUNK) {
           const int nv = std::min(GM_CHUNK, ndots - k0);
-          LAUNCH(h, k_multi_dot, nb, 256, 0, Vown, Vb, stride2, k0, nv, (const double2*)vec(j + 1), nb, gpart);
+          LAUNCH(h, k_multi_dot, nb, 256, 0, Vown, Vb, stride2, k0, nv, (const double2*)vec(j + 1), nb, gpart, wy);
         }
         CK(cudaGetLastError());
         CKR(reduce_to_host(h, gpart, ndots, h->gm_h, h->gm_h_host));
@@ -1047,7 +1085,7 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
         for (int k = 0; k <= j; ++k) { hcol[k] += h->gm_h_host[k]; hsq += h->gm_h_host[k] * h->gm_h_host[k]; }
         const double ww = fused ? h->gm_h_host[j + 1] : 0.0;
         // coefficients are already on the device in gm_h (all-reduced)
-        LAUNCH(h, k_gmres_update, nb, 256, 0, Vown, Vb, stride2, j + 1, h->gm_h, (double2*)vec(j + 1), nb, m + 1, gpart);
+        LAUNCH(h, k_gmres_update, nb, 256, 0, Vown, Vb, stride2, j + 1, h->gm_h, (double2*)vec(j + 1), nb, m + 1, gpart, wy);
         CK(cudaGetLastError());
         bool have_beta = false;
         if (fused && ww - hsq > h->gm_eta2 * ww) {

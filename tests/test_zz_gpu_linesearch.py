@@ -93,3 +93,41 @@ def test_residual_and_jacobian_at_extreme_latent_values(lib):
     # below the rounding level of the sums they sit in
     big = np.abs(vo) > 1e-14 * np.abs(vo).max()
     assert np.abs(vals[big] - vo[big]).max() <= 1e-9 * np.abs(vo[big]).max()
+
+
+@pytest.mark.parametrize("env", [{"LVPP_GMRES_WEIGHT": "auto"}, {"LVPP_GMRES_FUSED_NORM": "1"},
+                                 {"LVPP_GMRES_WEIGHT": "auto", "LVPP_GMRES_FUSED_NORM": "1"}])
+def test_experimental_gmres_switches_solve_the_same_system(lib, env, monkeypatch):
+    """The equilibrated residual norm and the one-reduction Gram-Schmidt (both off by default) change the Krylov
+    process, not the solution."""
+    import scipy.sparse.linalg as spla
+
+    import proximalgalerkin_b200 as lvpp
+    from oracle import mesh as omesh
+    from oracle import obstacle as oobs
+
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    n = 9
+    msh = lvpp.mesh.create_box(n, n, n)
+    opts_d = {"ksp_type": "gmres", "pc_type": "mg"}
+    s = lvpp.obstacle_pg.setup(msh, 1, petsc_options=opts_d)
+    dev = s["problem"].device_problem
+    orc = oobs.ObstacleOracle(omesh.box_kuhn(n, n, n))
+    rng = np.random.default_rng(3)
+    x = 0.2 * rng.standard_normal(orc.num_rows)
+    x[1::2] -= 30.0 * (rng.random(orc.num_rows // 2) > 0.7)  # a developed contact set: D ~ 0 on a third of the nodes
+    x[orc.bc_dofs] = 0.0
+    alpha = 5.0
+    dev.set_alpha(alpha)
+    dev.set_previous(np.zeros(orc.num_rows))
+    X, R, Y = (lvpp.DeviceVector(dev.n, dev.device) for _ in range(3))
+    X.set(x)
+    dev.assemble_jacobian(X)
+    rhs = rng.standard_normal(orc.num_rows)
+    R.set(rhs)
+    its, reason, _ = dev.linear_solve(R, Y, lvpp.newton_options(dict(opts_d, ksp_rtol=1e-12)))
+    assert reason > 0 and its < 120, (its, reason)
+    J = orc.jacobian(x, alpha)
+    ye = spla.splu(J.tocsc()).solve(rhs)
+    assert np.linalg.norm(Y.numpy() - ye) / np.linalg.norm(ye) < 1e-7

@@ -13,6 +13,7 @@ import time
 from pathlib import Path
 
 import numpy as np
+import scipy.sparse as sp
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
@@ -29,6 +30,9 @@ def main():
     ap.add_argument("--cheb", type=float, default=6.0)
     ap.add_argument("--outer", type=int, default=500)
     ap.add_argument("--restart", type=int, default=50)
+    ap.add_argument("--equilibrate", action="store_true",
+                    help="GMRES on S J S, S = diag(1, sqrt(a/m)) on (u, psi) with a, m the medians of alpha K_ii and M_ii: "
+                         "the residual norm weighs the psi rows by a/m (LVPP_GMRES_WEIGHT=auto in the library)")
     ap.add_argument("--snes-rtol", dest="snes_rtol", type=float, default=1e-6)
     args = ap.parse_args()
     n = args.size
@@ -48,7 +52,16 @@ def main():
             mg = mp.Multigrid(orc, x, alpha)
             mg.set_smoother(cheb=args.cheb)
             L0 = mg.levels[0]
-            yb, kits = mp.gmres_right(L0.J, lambda v: mg.cycle(v, 0, 1), mp.to_blocked(orc, F), rtol=1e-12, restart=args.restart, maxit=600)
+            rhs = mp.to_blocked(orc, F)
+            if args.equilibrate:
+                w = np.sqrt(np.median(alpha * L0.K.diagonal()) / np.median(L0.M.diagonal()))
+                Sd = np.concatenate([np.ones(N), np.full(N, w)])
+                S = sp.diags(Sd)
+                yt, kits = mp.gmres_right((S @ L0.J @ S).tocsr(), lambda v: mg.cycle(v / Sd, 0, 1) / Sd, Sd * rhs, rtol=1e-12,
+                                          restart=args.restart, maxit=600)
+                yb = Sd * yt
+            else:
+                yb, kits = mp.gmres_right(L0.J, lambda v: mg.cycle(v, 0, 1), rhs, rtol=1e-12, restart=args.restart, maxit=600)
             y = np.empty_like(x)
             y[orc.dof_u], y[orc.dof_psi] = yb[:N], yb[N:]
             x = x - y

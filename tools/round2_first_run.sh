@@ -6,7 +6,8 @@ mkdir -p gpurun_out
 (timeout 400 python -m pytest tests -m gpu -q -rxX 2>&1 | tail -15) | tee gpurun_out/r2_tests.txt
 python bench.py > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err; tail -1 gpurun_out/r2_bench.json | cut -c1-300
 echo "== experimental: one reduction per GMRES iteration"
-tools/mg_scan.sh "LVPP_GMRES_FUSED_NORM=0" "LVPP_GMRES_FUSED_NORM=1" "LVPP_MG_CHEB=10" "LVPP_MG_CHEB=4"
+tools/mg_scan.sh "LVPP_GMRES_FUSED_NORM=0" "LVPP_GMRES_FUSED_NORM=1" "LVPP_GMRES_WEIGHT=auto" "LVPP_GMRES_WEIGHT=auto LVPP_MG_CHEB=10" "LVPP_MG_CHEB=10" "LVPP_MG_CHEB=0"
+export LVPP_GMRES_WEIGHT=auto   # the equilibrated residual norm: 17-26 Krylov iterations through the whole 64^3 CPU emulation
 for cfg in "--linesearch none" "--linesearch bt" "--linesearch none --snes-rtol 1e-9" "--linesearch bt --snes-rtol 1e-9"; do
   tag=$(echo "$cfg" | tr -d ' -' )
   echo "== full solve n=215 $cfg"
