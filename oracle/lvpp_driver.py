@@ -189,3 +189,71 @@ def solve_signorini(problem, max_iterations=25, alpha_scheme="doubling", alpha_0
         u_prev = x[:nu].copy()
         problem.psi_k = x[nu:].copy()
     return x, {"it": it, "iterations": iterations}
+
+
+def solve_obstacle_adaptive(problem, max_outer=100, alpha_0=1.0, r=2.0, nfail_max=50, alpha_max=None, tol_exit=1e-6,
+                            snes_rtol=1e-6, snes_max_it=100, newton=None, verbose=False):
+    """The failure-recovering outer loop of the reference, written for the
+    obstacle problem.  Restates examples/03_fracture/fracture_dolfinx.py:215-283 (the same loop stands in
+    examples/07_eigenvalue_constraints/eigenvalue_constraints_dolfinx.py:163-225 and
+    examples/08_intersecting_constraints/intersecting_constraints_dolfinx.py:120-174):
+
+    * alpha starts at ``alpha_0`` (= 1, :215), r = 2 (:218), failures are counted in ``nfail`` (:219);
+    * a solve *fails* when SNES diverged (reason < 0, :239-240) or when it converged without doing a Newton step
+      (:234-238: alpha has been reduced so far that the initial guess satisfies the equation);
+    * on failure (:241-262): nfail += 1, alpha /= 2, the unknown goes back to the last accepted proximal iterate
+      (z_prev on the first proximal step, z_iter afterwards -- both are ``xk`` here, :250-253), give up when
+      nfail >= nfail_max (:255-260), else try again with the same k;
+    * on success: stop on the increment (:265-273; here the H1 increment of obstacle_pg.py:203,222); alpha *= r when
+      the solve took <= 4 Newton steps, alpha /= r when it took >= 10 (:276-279); z_iter <- z (:282); k += 1.
+
+    ``alpha_max`` (None in the reference loops) clamps alpha like obstacle_pg.py:184.  ``newton(x0, xk, alpha) ->
+    (x, reason, its)`` replaces the SNES solve (tests script failures with it).  Returns (x, history)."""
+    x = np.zeros(problem.num_rows)
+    xk = x.copy()
+    alpha = float(alpha_0)
+    hist = {k: [] for k in ("newton_steps", "alpha", "primal_increment", "reason", "attempts")}
+    k, nfail = 1, 0
+    gave_up = False
+
+    def snes_solve(x0, xk_, a):
+        xn, reason, n, _ = snes.newton_ls_none(lambda z: problem.assemble_residual(z, xk_, a), lambda z: problem.jacobian(z, a),
+                                               x0, rtol=snes_rtol, max_it=snes_max_it)
+        return xn, reason, n
+
+    newton = newton or snes_solve
+    while nfail <= nfail_max and k <= max_outer:
+        xn, reason, n = newton(x, xk, alpha)
+        hist["attempts"].append((k, alpha, int(n), int(reason)))
+        if reason < 0 or (n == 0 and reason > 0):
+            nfail += 1
+            if verbose:
+                print(f"failed to converge ({reason}), k={k} alpha={alpha}")
+            alpha /= 2
+            x = xk.copy()
+            if nfail >= nfail_max:
+                gave_up = True
+                break
+            continue
+        x = xn
+        obs = problem.observables(x, xk, alpha)
+        increment = float(np.sqrt(obs[4]))
+        hist["newton_steps"].append(int(n))
+        hist["alpha"].append(alpha)
+        hist["primal_increment"].append(increment)
+        hist["reason"].append(int(reason))
+        if verbose:
+            print(f"solved k={k} newton {n} alpha={alpha} increment {increment:.3e}")
+        if increment < tol_exit:
+            break
+        if n <= 4:
+            alpha *= r
+        elif n >= 10:
+            alpha /= r
+        if alpha_max is not None:
+            alpha = min(alpha, alpha_max)
+        xk = x.copy()
+        k += 1
+    hist["nfail"] = nfail
+    hist["gave_up"] = gave_up
+    return x, hist

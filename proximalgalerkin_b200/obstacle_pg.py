@@ -8,7 +8,7 @@ of the XDMF file name.  ``LvppStepper`` runs the same loop device-resident, one 
 """
 import numpy as np
 
-from . import fem
+from . import fem, recovery
 from .problem import NonlinearProblem, derivative, newton_options, obstacle_residual, DeviceVector
 
 
@@ -66,9 +66,14 @@ def setup(msh, polynomial_order=1, quadrature_degree=6, obstacle="phi_set", f_va
 
 
 def solve_problem(msh, polynomial_order=1, maximum_number_of_outer_loop_iterations=100, alpha_scheme="constant",
-                  alpha_max=1e5, tol_exit=1e-6, obstacle="phi_set", petsc_options=None, verbose=False):
+                  alpha_max=1e5, tol_exit=1e-6, obstacle="phi_set", petsc_options=None, verbose=False, adaptive=None):
     """Returns (sol, total Newton steps, history dict) -- the reference returns (sol, sum(Newton_steps))
-    and writes the history to CSV (obstacle_pg.py:245-264)."""
+    and writes the history to CSV (obstacle_pg.py:245-264).
+
+    ``alpha_scheme="adaptive"`` (not in obstacle_pg.py) replaces the fixed schedule by the
+    failure-recovering control of fracture_dolfinx.py:215-283: alpha doubles after a proximal step of <= 4 Newton steps,
+    halves after one of >= 10, and a failed Newton solve halves alpha, restores ``sol`` from ``sol_k`` and repeats
+    the step.  ``adaptive`` passes keyword arguments to ``recovery.AdaptiveAlpha`` (alpha_0, r, nfail_max)."""
     s = setup(msh, polynomial_order, obstacle=obstacle, petsc_options=petsc_options)
     sol, sol_k, alpha, problem = s["sol"], s["sol_k"], s["alpha"], s["problem"]
     dev = problem.device_problem
@@ -77,11 +82,35 @@ def solve_problem(msh, polynomial_order=1, maximum_number_of_outer_loop_iteratio
     alpha_k = 1
     hist = {k: [] for k in ("energy", "complementarity", "feasibility", "dual_feasibility", "newton_steps",
                             "alpha", "primal_increment", "latent_increment", "reason", "krylov_iterations")}
-    for k in range(maximum_number_of_outer_loop_iterations):
-        alpha.value, alpha_k = alpha_update(alpha_scheme, k, alpha.value, alpha_k, alpha_max)
-        problem.solve()
+    ctl = None
+    if alpha_scheme == "adaptive":  # the recovery loop of fracture_dolfinx.py:215-283 (recovery.py)
+        ctl = recovery.AdaptiveAlpha(alpha_max=alpha_max, **(adaptive or {}))
+        hist["attempts"] = ctl.attempts
+    k = 0
+    while k < maximum_number_of_outer_loop_iterations:
+        if ctl is None:
+            alpha.value, alpha_k = alpha_update(alpha_scheme, k, alpha.value, alpha_k, alpha_max)
+            problem.solve()
+        else:
+            alpha.value = ctl.alpha
+            try:
+                problem.solve()
+            except RuntimeError:  # *_error_if_not_converged: the reason is on the solver either way
+                pass
         reason = problem.solver.getConvergedReason()
         n = problem.solver.getIterationNumber()
+        if ctl is not None:
+            ctl.record(n, reason)
+            if ctl.is_failure(reason, n):
+                if verbose and msh.rank == 0:
+                    print(f"Failed to converge ({reason}), k={ctl.k} alpha={alpha.value}")
+                sol.x.array[:] = sol_k.x.array[:]  # back to the last accepted proximal iterate (:250-253)
+                try:
+                    ctl.failed()
+                except recovery.GaveUp:
+                    hist["gave_up"] = True
+                    break
+                continue
         # observables (obstacle_pg.py:196-201): evaluated on the device at the iterate just computed
         dev.x.set(sol.x.array)
         obs = dev.observables(dev.x)
@@ -101,7 +130,10 @@ def solve_problem(msh, polynomial_order=1, maximum_number_of_outer_loop_iteratio
                   f"Increment size: {increment}")
         if increment < tol_exit:
             break
+        if ctl is not None:
+            ctl.accepted(n)
         sol_k.x.array[:] = sol.x.array[:]
+        k += 1
     return sol, sum(hist["newton_steps"]), hist
 
 
@@ -111,7 +143,7 @@ class LvppStepper:
 
     def __init__(self, msh, polynomial_order=1, alpha_scheme="double_exponential", alpha_max=1e2, tol_exit=1e-4,
                  max_outer=500, obstacle="phi_set", petsc_options=None, setup_objects=None, obstacle_period=None,
-                 obstacle_origin=0.0):
+                 obstacle_origin=0.0, adaptive=None):
         s = setup_objects or setup(msh, polynomial_order, obstacle=obstacle, petsc_options=petsc_options,
                                    obstacle_period=obstacle_period, obstacle_origin=obstacle_origin)
         self.s = s
@@ -131,6 +163,10 @@ class LvppStepper:
         self.total_krylov = 0
         self.finished = False
         self.history = {k: [] for k in ("newton_steps", "alpha", "primal_increment", "reason")}
+        # alpha_scheme "adaptive": failure-recovering control of fracture_dolfinx.py:215-283 (recovery.py)
+        self.ctl = recovery.AdaptiveAlpha(alpha_max=alpha_max, **(adaptive or {})) if alpha_scheme == "adaptive" else None
+        if self.ctl is not None:
+            self.history["attempts"] = self.ctl.attempts
         self.nb, self.last_lambda = None, 1.0
         if self.opts.snes_linesearch != 0:
             from . import linesearch
@@ -141,7 +177,10 @@ class LvppStepper:
         self._begin_outer()
 
     def _begin_outer(self):
-        self.alpha_value, self.alpha_k = alpha_update(self.alpha_scheme, self.k, self.alpha_value, self.alpha_k, self.alpha_max)
+        if self.ctl is not None:
+            self.alpha_value = self.ctl.alpha
+        else:
+            self.alpha_value, self.alpha_k = alpha_update(self.alpha_scheme, self.k, self.alpha_value, self.alpha_k, self.alpha_max)
         self.dev.set_alpha(self.alpha_value)
         self.dev.set_previous(self.xk)
         if self.nb is not None:  # snes_linesearch_type bt: host loop over the library's entry points
@@ -188,6 +227,19 @@ class LvppStepper:
                 reason = -5
         if reason == 0:
             return True
+        if self.ctl is not None:
+            self.ctl.record(self.newton_its, reason)
+            if self.ctl.is_failure(reason, self.newton_its):
+                # halve alpha, go back to the last accepted proximal iterate, repeat the step (:241-262)
+                self.x.tensor.copy_(self.xk.tensor)
+                try:
+                    self.ctl.failed()
+                except recovery.GaveUp:
+                    self.finished = True
+                    self.history["gave_up"] = True
+                    return False
+                self._begin_outer()
+                return True
         if reason < 0:
             raise RuntimeError(f"SNES did not converge: reason {reason}")
         obs = self.dev.observables(self.x)
@@ -200,6 +252,8 @@ class LvppStepper:
         if increment < self.tol_exit or self.k >= self.max_outer:
             self.finished = True
             return False
+        if self.ctl is not None:
+            self.ctl.accepted(self.newton_its)
         self.xk.tensor.copy_(self.x.tensor)
         self._begin_outer()
         return True

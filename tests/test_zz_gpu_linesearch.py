@@ -131,3 +131,33 @@ def test_experimental_gmres_switches_solve_the_same_system(lib, env, monkeypatch
     J = orc.jacobian(x, alpha)
     ye = spla.splu(J.tocsc()).solve(rhs)
     assert np.linalg.norm(Y.numpy() - ye) / np.linalg.norm(ye) < 1e-7
+
+
+@pytest.mark.parametrize("max_it", [100, 5])
+def test_adaptive_alpha_with_recovery_matches_oracle(lib, max_it):
+    """alpha_scheme="adaptive" (recovery.py): host-buffer driver and device-resident stepper against the
+    restated loop of fracture_dolfinx.py:215-283.  snes_max_it = 5 makes the first proximal step fail at alpha = 1
+    (reason -5), so the halve-restore-retry branch runs on real arithmetic."""
+    import proximalgalerkin_b200 as lvpp
+    from oracle import lvpp_driver
+    from oracle import mesh as omesh
+    from oracle import obstacle as oobs
+
+    n = 8
+    orc = oobs.ObstacleOracle(omesh.box_kuhn(n, n, n))
+    xo, ho = lvpp_driver.solve_obstacle_adaptive(orc, max_outer=40, alpha_max=1e5, tol_exit=1e-4, nfail_max=12, snes_max_it=max_it)
+    opts = {"ksp_type": "gmres", "pc_type": "mg", "ksp_rtol": 1e-12, "snes_max_it": max_it,
+            "snes_error_if_not_converged": False, "ksp_error_if_not_converged": False}
+    msh = lvpp.mesh.create_box(n, n, n)
+    sol, total, h = lvpp.obstacle_pg.solve_problem(msh, 1, 40, "adaptive", 1e5, 1e-4, petsc_options=opts, adaptive=dict(nfail_max=12))
+    assert [tuple(a) for a in h["attempts"]] == [tuple(a) for a in ho["attempts"]]
+    assert h["alpha"] == ho["alpha"]
+    u, uo = sol.x.array[0::2], xo[0::2]
+    assert np.linalg.norm(u - uo) <= 1e-10 * np.linalg.norm(uo)
+    st = lvpp.obstacle_pg.LvppStepper(msh, 1, "adaptive", 1e5, 1e-4, max_outer=40, petsc_options=opts, adaptive=dict(nfail_max=12))
+    while st.step():
+        pass
+    assert [tuple(a) for a in st.history["attempts"]] == [tuple(a) for a in ho["attempts"]]
+    assert st.history["newton_steps"] == ho["newton_steps"]
+    us = st.x.numpy()[0::2]
+    assert np.linalg.norm(us - uo) <= 1e-10 * np.linalg.norm(uo)

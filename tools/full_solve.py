@@ -24,6 +24,10 @@ def main():
                          "||F_psi|| * O(h^-5): DESIGN.md 7a)")
     ap.add_argument("--linesearch", default="none", choices=["none", "bt"],
                     help="bt: PETSc's backtracking line search (the full step overshoots on fine 3-D meshes)")
+    ap.add_argument("--alpha-scheme", dest="alpha_scheme", default="double_exponential",
+                    choices=["double_exponential", "adaptive", "constant", "geometric"],
+                    help="adaptive: alpha x2 / :2 by Newton count, halved and the step repeated when a Newton solve fails "
+                         "(proximalgalerkin_b200/recovery.py; the reference's remedy in examples 03, 07, 08)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -42,7 +46,9 @@ def main():
     opts["snes_linesearch_type"] = args.linesearch
     if args.snes_rtol is not None:
         opts["snes_rtol"] = args.snes_rtol
-    st = lvpp.obstacle_pg.LvppStepper(msh, 1, "double_exponential", 1e2, 1e-4, petsc_options=opts)
+    if args.alpha_scheme == "adaptive":  # a failed solve is reported as a reason, not raised
+        opts.update({"snes_error_if_not_converged": False, "ksp_error_if_not_converged": False})
+    st = lvpp.obstacle_pg.LvppStepper(msh, 1, args.alpha_scheme, 1e2, 1e-4, petsc_options=opts)
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t0
     t1 = time.perf_counter()
@@ -74,7 +80,7 @@ def main():
     s = st.dev.stats()
     if rank == 0:
         print(json.dumps({
-            "workload": f"3-D P1 obstacle LVPP, {n}x{n}x{nz} cubes x 6 tets, full solve (double-exponential alpha, alpha_max 1e2, tol 1e-4)",
+            "workload": f"3-D P1 obstacle LVPP, {n}x{n}x{nz} cubes x 6 tets, full solve ({args.alpha_scheme} alpha, alpha_max 1e2, tol 1e-4)",
             "n_gpus": world, "rows": s["num_rows"], "setup_s": t_setup, "solve_s": t_solve,
             "newton_steps": st.total_newton, "krylov_iterations": st.total_krylov, "outer_steps": len(st.history["newton_steps"]),
             "dofs_per_sec": s["num_rows"] * st.total_newton / t_solve, "history": st.history,

@@ -15,3 +15,7 @@ for cfg in "--linesearch none" "--linesearch bt" "--linesearch none --snes-rtol 
   grep -E "^outer|Chebyshev ratio|retrying|Error" gpurun_out/r2_full215_$tag.err | tail -40
   tail -1 gpurun_out/r2_full215_$tag.json | cut -c1-600
 done
+echo "== full solve n=215, failure-recovering alpha control (recovery.py)"
+LVPP_MG_VERBOSE=1 timeout 300 python tools/full_solve.py --size 215 --verbose --alpha-scheme adaptive > gpurun_out/r2_full215_adaptive.json 2> gpurun_out/r2_full215_adaptive.err
+grep -E "^outer|retrying|Error" gpurun_out/r2_full215_adaptive.err | tail -40
+tail -1 gpurun_out/r2_full215_adaptive.json | cut -c1-800
