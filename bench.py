@@ -286,12 +286,15 @@ def run_b200(args):
     roof_extra = None
     if n_p:
         sm_ms = (s1["smooth_sampled_ms"] - s0["smooth_sampled_ms"]) / n_p
-        sm_bytes = 16 * slots + (16 + 16 + 32 + 16 + 1 + 0.25) * V_own
+        # (LVPP_MG_PACK=bf16, experimental: 20-byte records per pair of slots, kernel k_packed2_op)
+        rec = 10 if os.environ.get("LVPP_MG_PACK") == "bf16" and os.environ.get("LVPP_MG_FP32", "1") != "0" else 16
+        sm_bytes = rec * slots + (16 + 16 + 32 + 16 + 1 + 0.25) * V_own
         roofline = {
-            "bound": "hbm", "kernel": "k_packed_op (multigrid smoother sweep on the fine level: packed {col, alpha K, M, D} "
-                                      "single-precision records, fp64 accumulation, fused node-block Jacobi update)",
+            "bound": "hbm", "kernel": ("k_packed2_op (multigrid smoother sweep on the fine level: bf16 pair records, 10 B / slot, " if rec == 10 else
+                                       "k_packed_op (multigrid smoother sweep on the fine level: packed {col, alpha K, M, D} "
+                                       "single-precision records, ") + "fp64 accumulation, fused node-block Jacobi update)",
             "achieved": sm_bytes / (sm_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": sm_bytes / (sm_ms * 1e-3) / 1e9 / peak,
-            "traffic": traffic_of("smooth_traffic.json"), "peak_source": peak_src, "algorithmic_bytes_per_launch": sm_bytes,
+            "traffic": traffic_of("smooth_traffic.json") if rec == 16 else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": sm_bytes,
             "ms_per_launch": sm_ms, "launches_sampled": n_p, "launches_in_timed_region": packed_ops,
             "share_of_step": sm_ms * packed_ops / (secs * 1e3) if secs > 0 else None,
         }

@@ -193,6 +193,111 @@ __global__ void __launch_bounds__(256, MINB) k_packed_op(PackedOpArgs p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Experimental (LVPP_MG_PACK=bf16, off by default): bf16 values, one record per PAIR of consecutive slots of a row --
+// a 128-bit load {col0, col1, bf16(alpha K0)|bf16(M0), bf16(alpha K1)|bf16(M1)} and a 32-bit load bf16(D0)|bf16(D1):
+// 10 instead of 16 bytes per slot (the fine-level sweep at n = 215: 3.22 -> 2.31 GB).  bf16 keeps the exponent range
+// of the single-precision records (D = int exp(psi) phi_i phi_j spans 26 orders of magnitude) and 8 bits of mantissa;
+// on the CPU mirror of the cycle (tools/mg_precision.py) the Krylov iteration counts of the first four proximal steps
+// are those of the fp64 cycle (360 against 359 in total on a 16^3 mesh) -- the cycle only has to be a fixed linear map
+// close to J^-1.  Pair p of slice s sits at ((slice_ptr[s] + 32 s) >> 1) + 32 p + lane: rows of odd width get a zero
+// second slot, no second pointer array is needed (16 records per slice of even width are left unused).
+struct Packed2OpArgs {
+  int64_t Vown;
+  const int64_t* slice_ptr;
+  const uint4* P2;
+  const uint32_t* Pd;
+  const uint8_t* bc_flag;
+  const double2* v;
+  double2* y;
+  int epi;
+  const double2* b;
+  const double* binv;
+  double omega;
+};
+
+__device__ __forceinline__ uint32_t lvpp_ld_u32(const uint32_t* ptr) {
+  uint32_t r;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(ptr));
+  return r;
+}
+__device__ __forceinline__ double lvpp_bf16_hi(uint32_t w) { return (double)__uint_as_float(w & 0xFFFF0000u); }
+__device__ __forceinline__ double lvpp_bf16_lo(uint32_t w) { return (double)__uint_as_float(w << 16); }
+
+template <int UP, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_packed2_op(Packed2OpArgs p) {
+  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x; i0 < p.Vown; i0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = i0 + threadIdx.x;
+    if (i >= p.Vown) continue;
+    const int64_t s = i >> 5;
+    const int64_t b0 = p.slice_ptr[s];
+    const int w = (int)((p.slice_ptr[s + 1] - b0) >> 5);
+    const int np = (w + 1) >> 1;  // pair records of this row, >= 1
+    const int64_t po = ((b0 + 32 * s) >> 1) + (i & 31);
+    const uint4* q = p.P2 + po;
+    const uint32_t* qd = p.Pd + po;
+    uint4 cur[UP];
+    uint32_t curd[UP];
+#pragma unroll
+    for (int u = 0; u < UP; ++u) {
+      const int64_t off = (int64_t)min(u, np - 1) * LVPP_SLICE;
+      cur[u] = lvpp_ld_record(q + off);
+      curd[u] = lvpp_ld_u32(qd + off);
+    }
+    double au = 0.0, ap = 0.0;
+    for (int k0 = 0; k0 < np; k0 += UP) {
+      uint4 nxt[UP];
+      uint32_t nxtd[UP];
+#pragma unroll
+      for (int u = 0; u < UP; ++u) {
+        const int64_t off = (int64_t)min(k0 + UP + u, np - 1) * LVPP_SLICE;
+        nxt[u] = lvpp_ld_record(q + off);
+        nxtd[u] = lvpp_ld_u32(qd + off);
+      }
+      double2 va[UP], vb[UP];
+#pragma unroll
+      for (int u = 0; u < UP; ++u) {
+        va[u] = lvpp_ld_pair(&p.v[cur[u].x & ~LVPP_COL_BC]);
+        vb[u] = lvpp_ld_pair(&p.v[cur[u].y & ~LVPP_COL_BC]);
+      }
+#pragma unroll
+      for (int u = 0; u < UP; ++u) {
+        const bool live = k0 + u < np;  // records past the end of the row were re-reads of the last one
+        const uint32_t km0 = live ? cur[u].z : 0u, km1 = live ? cur[u].w : 0u, dd = live ? curd[u] : 0u;
+        const double vx0 = (cur[u].x & LVPP_COL_BC) ? 0.0 : va[u].x;
+        const double vx1 = (cur[u].y & LVPP_COL_BC) ? 0.0 : vb[u].x;
+        au += lvpp_bf16_hi(km0) * vx0 + lvpp_bf16_lo(km0) * va[u].y;
+        ap += lvpp_bf16_lo(km0) * vx0 - lvpp_bf16_hi(dd) * va[u].y;
+        au += lvpp_bf16_hi(km1) * vx1 + lvpp_bf16_lo(km1) * vb[u].y;
+        ap += lvpp_bf16_lo(km1) * vx1 - lvpp_bf16_lo(dd) * vb[u].y;
+      }
+#pragma unroll
+      for (int u = 0; u < UP; ++u) {
+        cur[u] = nxt[u];
+        curd[u] = nxtd[u];
+      }
+    }
+    const double2 vi = p.v[i];
+    const bool isbc = p.bc_flag[i] != 0;
+    double2 out;
+    out.x = isbc ? vi.x : au;
+    out.y = ap;
+    if (p.epi != EPI_NONE) {
+      const double2 bi = p.b[i];
+      const double ru = bi.x - out.x, rp = bi.y - out.y;
+      if (p.epi == EPI_RESID) {
+        out.x = ru;
+        out.y = rp;
+      } else {
+        const double* B = p.binv + 4 * i;
+        out.x = vi.x + (isbc ? 1.0 : p.omega) * (B[0] * ru + B[1] * rp);
+        out.y = vi.y + p.omega * (B[2] * ru + B[3] * rp);
+      }
+    }
+    p.y[i] = out;
+  }
+}
+
 static inline OpArgs lvpp_level_op(const lvpp_problem* h, const MgLevel& L) {
   OpArgs p;
   p.Vown = L.Vown; p.slice_ptr = L.slice_ptr; p.col = L.col;

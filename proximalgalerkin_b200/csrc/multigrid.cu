@@ -18,6 +18,7 @@
 // Gram-Schmidt with selective re-orthogonalisation; Hessenberg/Givens on the host, two small D2H
 // reads per iteration; all reductions deterministic).
 #include <cub/cub.cuh>
+#include <cuda_bf16.h>
 
 #include <cmath>
 #include <cstring>
@@ -357,6 +358,34 @@ __global__ void k_pack_op(int64_t n, const uint32_t* __restrict__ col, const dou
                       __float_as_uint((float)fmin(D[i], big)));
 }
 
+// bf16 pair records of the experimental cycle operator (block_op.cuh: k_packed2_op); one warp per slice
+__device__ __forceinline__ uint32_t lvpp_bf16_pair(float hi, float lo) {
+  return ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(hi)) << 16) | (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(lo));
+}
+__global__ void __launch_bounds__(256) k_pack_op_bf16(int64_t nslices, const int64_t* __restrict__ slice_ptr,
+                                                      const uint32_t* __restrict__ col, const double* __restrict__ K,
+                                                      const double* __restrict__ M, const double* __restrict__ D, double alpha,
+                                                      uint4* __restrict__ P2, uint32_t* __restrict__ Pd) {
+  const double big = 3.0e38;  // as k_pack_op: no inf in the records (bf16 has the exponent range of fp32)
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t s = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; s < nslices; s += nwarps) {
+    const int64_t b0 = slice_ptr[s];
+    const int w = (int)((slice_ptr[s + 1] - b0) >> 5);
+    const int64_t po = ((b0 + 32 * s) >> 1) + lane;
+    for (int k = 0; k < w; k += 2) {
+      const int64_t i0 = b0 + lane + (int64_t)k * LVPP_SLICE;
+      const bool two = k + 1 < w;
+      const int64_t i1 = two ? i0 + LVPP_SLICE : i0;  // rows of odd width: a zero second slot on the first one's column
+      const float k0 = (float)fmin(fmax(alpha * K[i0], -big), big), m0 = (float)M[i0], d0 = (float)fmin(D[i0], big);
+      const float k1 = two ? (float)fmin(fmax(alpha * K[i1], -big), big) : 0.f, m1 = two ? (float)M[i1] : 0.f,
+                  d1 = two ? (float)fmin(D[i1], big) : 0.f;
+      P2[po + (int64_t)(k >> 1) * LVPP_SLICE] = make_uint4(col[i0], col[i1], lvpp_bf16_pair(k0, m0), lvpp_bf16_pair(k1, m1));
+      Pd[po + (int64_t)(k >> 1) * LVPP_SLICE] = lvpp_bf16_pair(d0, d1);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // hierarchy construction
 static int reduce_to_host(lvpp_problem* h, double* partials, int nvals, double* dst_dev, double* dst_host);
@@ -686,8 +715,18 @@ int lvpp_mg_setup(lvpp_problem* h) {
     if (stop) break;
   }
   h->mg_fp32 = env_double("LVPP_MG_FP32", 1.0) != 0.0;
+  if (const char* pk = getenv("LVPP_MG_PACK")) h->mg_bf16 = h->mg_fp32 && strcmp(pk, "bf16") == 0;
   if (h->mg_fp32)
-    for (size_t l = 0; l + 1 < h->levels.size(); ++l) CKR(lvpp_dalloc(h, &h->levels[l].P, (size_t)h->levels[l].slots, false));
+    for (size_t l = 0; l + 1 < h->levels.size(); ++l) {
+      MgLevel& L = h->levels[l];
+      if (h->mg_bf16) {  // pair records: slots / 2 + 16 per slice (block_op.cuh)
+        const size_t npairs = (size_t)(L.slots >> 1) + 16 * (size_t)L.nslices;
+        CKR(lvpp_dalloc(h, &L.P2, npairs, false));
+        CKR(lvpp_dalloc(h, &L.Pd, npairs, false));
+      } else {
+        CKR(lvpp_dalloc(h, &L.P, (size_t)L.slots, false));
+      }
+    }
   // coarsest level: global numbering of all ranks' coarse nodes, rank by rank
   const MgLevel& Lc = h->levels.back();
   std::vector<double> cnt((size_t)h->nranks, 0.0);
@@ -730,7 +769,21 @@ static int level_op_local(lvpp_problem* h, MgLevel& L, int epi, double omega, co
                          double* y, bool f32 = false) {
   const int grid = lvpp_grid(L.Vown, 256, 6);
   if (&L == &h->levels[0]) h->fine_op_launches++;
-  if (f32 && L.P) {
+  if (f32 && L.P2) {
+    Packed2OpArgs q;
+    q.Vown = L.Vown; q.slice_ptr = L.slice_ptr; q.P2 = L.P2; q.Pd = L.Pd; q.bc_flag = L.bc_flag;
+    q.v = (const double2*)v; q.y = (double2*)y; q.epi = epi; q.b = (const double2*)b; q.binv = L.binv; q.omega = omega;
+    const bool sample = &L == &h->levels[0] && epi == EPI_JACOBI && h->smooth_sample_pending;
+    if (sample) CK(cudaEventRecord(h->evp0, h->stream));
+    if (h->mg_unroll == 8) LAUNCH(h, (k_packed2_op<4, 3>), lvpp_grid(L.Vown, 256, 3), 256, 0, q);
+    else LAUNCH(h, (k_packed2_op<2, 4>), lvpp_grid(L.Vown, 256, 4), 256, 0, q);
+    if (&L == &h->levels[0]) h->packed_op_launches++;
+    if (sample) {
+      CK(cudaEventRecord(h->evp1, h->stream));
+      h->smooth_sample_pending = false;
+      h->smooth_sample_recorded = true;
+    }
+  } else if (f32 && L.P) {
     PackedOpArgs q;
     q.Vown = L.Vown; q.slice_ptr = L.slice_ptr; q.P = L.P; q.bc_flag = L.bc_flag;
     q.v = (const double2*)v; q.y = (double2*)y; q.epi = epi; q.b = (const double2*)b; q.binv = L.binv; q.omega = omega;
@@ -843,7 +896,11 @@ int lvpp_mg_update(lvpp_problem* h) {
   if (h->mg_fp32)
     for (int l = 0; l + 1 < nl; ++l) {
       MgLevel& L = h->levels[l];
-      LAUNCH(h, k_pack_op, lvpp_grid(L.slots, 256, 16), 256, 0, L.slots, L.col, L.K, L.M, L.D, h->alpha, L.P);
+      if (L.P2)
+        LAUNCH(h, k_pack_op_bf16, lvpp_grid(32 * L.nslices, 256, 16), 256, 0, L.nslices, L.slice_ptr, L.col, L.K, L.M, L.D,
+               h->alpha, L.P2, L.Pd);
+      else
+        LAUNCH(h, k_pack_op, lvpp_grid(L.slots, 256, 16), 256, 0, L.slots, L.col, L.K, L.M, L.D, h->alpha, L.P);
       CK(cudaGetLastError());
     }
   // lambda_max(Binv J) is set by the stiffness block (mesh and element, much less by psi), so it is estimated when

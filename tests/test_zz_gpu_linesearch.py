@@ -96,10 +96,11 @@ def test_residual_and_jacobian_at_extreme_latent_values(lib):
 
 
 @pytest.mark.parametrize("env", [{"LVPP_GMRES_WEIGHT": "auto"}, {"LVPP_GMRES_FUSED_NORM": "1"},
-                                 {"LVPP_GMRES_WEIGHT": "auto", "LVPP_GMRES_FUSED_NORM": "1"}])
+                                 {"LVPP_GMRES_WEIGHT": "auto", "LVPP_GMRES_FUSED_NORM": "1"},
+                                 {"LVPP_MG_PACK": "bf16"}, {"LVPP_MG_PACK": "bf16", "LVPP_MG_UNROLL": "8"}])
 def test_experimental_gmres_switches_solve_the_same_system(lib, env, monkeypatch):
-    """The equilibrated residual norm and the one-reduction Gram-Schmidt (both off by default) change the Krylov
-    process, not the solution."""
+    """The equilibrated residual norm, the one-reduction Gram-Schmidt and the bf16 pair records of the cycle operator
+    (all off by default) change the Krylov process or the preconditioner, not the solution."""
     import scipy.sparse.linalg as spla
 
     import proximalgalerkin_b200 as lvpp
