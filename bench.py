@@ -288,7 +288,7 @@ def run_b200(args):
         sm_ms = (s1["smooth_sampled_ms"] - s0["smooth_sampled_ms"]) / n_p
         # (LVPP_MG_PACK=bf16, experimental: 20-byte records per pair of slots, kernel k_packed2_op)
         rec = 10 if os.environ.get("LVPP_MG_PACK") == "bf16" and os.environ.get("LVPP_MG_FP32", "1") != "0" else 16
-        sm_bytes = rec * slots + (16 + 16 + 32 + 16 + 1 + 0.25) * V_own
+        sm_bytes = rec * slots + (16 + 16 + (16 if rec == 10 else 32) + 16 + 1 + 0.25) * V_own
         roofline = {
             "bound": "hbm", "kernel": ("k_packed2_op (multigrid smoother sweep on the fine level: bf16 pair records, 10 B / slot, " if rec == 10 else
                                        "k_packed_op (multigrid smoother sweep on the fine level: packed {col, alpha K, M, D} "

@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(256, MINB) k_packed_op(PackedOpArgs p) {
 // ------------------------------------------------------------------------------------------------
 // Experimental (LVPP_MG_PACK=bf16, off by default): bf16 values, one record per PAIR of consecutive slots of a row --
 // a 128-bit load {col0, col1, bf16(alpha K0)|bf16(M0), bf16(alpha K1)|bf16(M1)} and a 32-bit load bf16(D0)|bf16(D1):
-// 10 instead of 16 bytes per slot (the fine-level sweep at n = 215: 3.22 -> 2.31 GB).  bf16 keeps the exponent range
+// 10 instead of 16 bytes per slot, and the node-block inverses in single precision (16 instead of 32 bytes per node):
+// the fine-level sweep at n = 215 moves 2.15 instead of 3.22 GB.  bf16 keeps the exponent range
 // of the single-precision records (D = int exp(psi) phi_i phi_j spans 26 orders of magnitude) and 8 bits of mantissa;
 // on the CPU mirror of the cycle (tools/mg_precision.py) the Krylov iteration counts of the first four proximal steps
 // are those of the fp64 cycle (360 against 359 in total on a 16^3 mesh) -- the cycle only has to be a fixed linear map
@@ -212,7 +213,7 @@ struct Packed2OpArgs {
   double2* y;
   int epi;
   const double2* b;
-  const double* binv;
+  const float4* binv;    // [Vown] single-precision node-block inverses
   double omega;
 };
 
@@ -289,9 +290,9 @@ __global__ void __launch_bounds__(256, MINB) k_packed2_op(Packed2OpArgs p) {
         out.x = ru;
         out.y = rp;
       } else {
-        const double* B = p.binv + 4 * i;
-        out.x = vi.x + (isbc ? 1.0 : p.omega) * (B[0] * ru + B[1] * rp);
-        out.y = vi.y + p.omega * (B[2] * ru + B[3] * rp);
+        const float4 B = p.binv[i];
+        out.x = vi.x + (isbc ? 1.0 : p.omega) * ((double)B.x * ru + (double)B.y * rp);
+        out.y = vi.y + p.omega * ((double)B.z * ru + (double)B.w * rp);
       }
     }
     p.y[i] = out;

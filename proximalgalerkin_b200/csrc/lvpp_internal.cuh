@@ -96,6 +96,7 @@ struct MgLevel {
   // experimental bf16 copy (LVPP_MG_PACK=bf16): one record per PAIR of slots, 20 bytes (block_op.cuh: k_packed2_op)
   uint4* P2 = nullptr;           // {col0, col1, bf16(alpha K0) | bf16(M0), bf16(alpha K1) | bf16(M1)}
   uint32_t* Pd = nullptr;        // bf16(D0) | bf16(D1)
+  float4* binv32 = nullptr;      // [Vown] single-precision copy of binv for k_packed2_op
   uint8_t* bc_flag = nullptr;    // [V] u dof of the node is inactive (Dirichlet / all-Dirichlet aggregate)
   int32_t* box = nullptr;        // [Vown * 3] integer box coordinates used by the coordinate aggregation
   // transfer to the next coarser level

@@ -185,7 +185,8 @@ __global__ void k_galerkin(int64_t nnzc, const int64_t* __restrict__ gal_ptr, co
 // cycle kernels
 __global__ void k_build_binv(int64_t Vown, const int64_t* __restrict__ slice_ptr, const uint8_t* __restrict__ diag_k,
                              const double* __restrict__ K, const double* __restrict__ M, const double* __restrict__ D,
-                             const uint8_t* __restrict__ bc, double alpha, double* __restrict__ binv) {
+                             const uint8_t* __restrict__ bc, double alpha, double* __restrict__ binv,
+                             float4* __restrict__ binv32) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vown; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t idx = slice_ptr[i >> 5] + (i & 31) + (int64_t)diag_k[i] * LVPP_SLICE;
     const double a = alpha * K[idx], m = M[idx], d = D[idx];
@@ -195,6 +196,11 @@ __global__ void k_build_binv(int64_t Vown, const int64_t* __restrict__ slice_ptr
     } else {
       const double idet = 1.0 / (-a * d - m * m);
       B[0] = -d * idet; B[1] = -m * idet; B[2] = -m * idet; B[3] = a * idet;
+    }
+    if (binv32) {  // single-precision copy read by k_packed2_op (clamped: 1 / D leaves the range at psi < -70)
+      const double big = 3.0e38;
+      binv32[i] = make_float4((float)fmin(fmax(B[0], -big), big), (float)fmin(fmax(B[1], -big), big),
+                              (float)fmin(fmax(B[2], -big), big), (float)fmin(fmax(B[3], -big), big));
     }
   }
 }
@@ -723,6 +729,7 @@ int lvpp_mg_setup(lvpp_problem* h) {
         const size_t npairs = (size_t)(L.slots >> 1) + 16 * (size_t)L.nslices;
         CKR(lvpp_dalloc(h, &L.P2, npairs, false));
         CKR(lvpp_dalloc(h, &L.Pd, npairs, false));
+        CKR(lvpp_dalloc(h, &L.binv32, (size_t)L.Vown, false));
       } else {
         CKR(lvpp_dalloc(h, &L.P, (size_t)L.slots, false));
       }
@@ -772,7 +779,7 @@ static int level_op_local(lvpp_problem* h, MgLevel& L, int epi, double omega, co
   if (f32 && L.P2) {
     Packed2OpArgs q;
     q.Vown = L.Vown; q.slice_ptr = L.slice_ptr; q.P2 = L.P2; q.Pd = L.Pd; q.bc_flag = L.bc_flag;
-    q.v = (const double2*)v; q.y = (double2*)y; q.epi = epi; q.b = (const double2*)b; q.binv = L.binv; q.omega = omega;
+    q.v = (const double2*)v; q.y = (double2*)y; q.epi = epi; q.b = (const double2*)b; q.binv = L.binv32; q.omega = omega;
     const bool sample = &L == &h->levels[0] && epi == EPI_JACOBI && h->smooth_sample_pending;
     if (sample) CK(cudaEventRecord(h->evp0, h->stream));
     if (h->mg_unroll == 8) LAUNCH(h, (k_packed2_op<4, 3>), lvpp_grid(L.Vown, 256, 3), 256, 0, q);
@@ -820,7 +827,7 @@ static int level_op(lvpp_problem* h, MgLevel& L, int epi, double omega, const do
 
 static int build_binv(lvpp_problem* h, MgLevel& L) {
   LAUNCH(h, k_build_binv, lvpp_grid(L.Vown, 256, 8), 256, 0, L.Vown, L.slice_ptr, L.diag_k, L.K, L.M, L.D,
-         L.bc_flag, h->alpha, L.binv);
+         L.bc_flag, h->alpha, L.binv, L.binv32);
   CK(cudaGetLastError());
   return 0;
 }
