@@ -44,7 +44,10 @@ class ObstacleOracle:
         self.degree = degree
         self.f = float(f)
         cell = mesh.cell_name
-        self.qpts, self.qwts = make_quadrature(cell, quadrature_degree, scheme)
+        if isinstance(scheme, (tuple, list)):  # an explicit rule (points [nq, tdim], weights [nq]), e.g. basix's, exported
+            self.qpts, self.qwts = (np.asarray(a, dtype=np.float64) for a in scheme)  # by tools/export_from_dolfinx.py
+        else:
+            self.qpts, self.qwts = make_quadrature(cell, quadrature_degree, scheme)
         self.phi_tab, self.dphi_tab = elements.tabulate(degree, self.qpts)
         self.cell_nodes, self.num_nodes, self.node_coords = elements.build_nodes(mesh, degree)
         self.nld = self.cell_nodes.shape[1]

@@ -41,9 +41,11 @@ PETSC_OPTIONS = {  # obstacle_pg.py:128-139
 
 
 def setup(msh, polynomial_order=1, quadrature_degree=6, obstacle="phi_set", f_value=0.0, petsc_options=None,
-          obstacle_period=None, obstacle_origin=0.0):
-    """Everything obstacle_pg.py builds before the outer loop.  Returns a dict of the objects."""
-    V = fem.functionspace(msh, ("Lagrange", polynomial_order), quadrature_degree=quadrature_degree)
+          obstacle_period=None, obstacle_origin=0.0, rule=None):
+    """Everything obstacle_pg.py builds before the outer loop.  Returns a dict of the objects.
+    ``rule``: explicit quadrature rule (points, weights) instead of the table of ``quadrature_degree`` -- e.g.
+    basix's, exported by tools/export_from_dolfinx.py."""
+    V = fem.functionspace(msh, ("Lagrange", polynomial_order), quadrature_degree=quadrature_degree, rule=rule)
     alpha = fem.Constant(msh, 1.0)
     f = fem.Constant(msh, f_value)
     dofs = fem.locate_dofs_boundary(V.sub(0))
