@@ -134,8 +134,9 @@ def linesearch_bt(residual, x, F, y, fnorm, Jy, alpha=1e-4, maxstep=1e8, steptol
     return w, G, gnorm, lam, False
 
 
-def newton_ls(residual, jacobian, x0, linesearch="none", rtol=1e-8, atol=1e-50, stol=1e-8, max_it=50, divtol=1e4):
-    """SNESSolve_NEWTONLS with line search "none" (basic, full step) or "bt".  Returns (x, reason, its, hist)."""
+def newton_ls(residual, jacobian, x0, linesearch="none", rtol=1e-8, atol=1e-50, stol=1e-8, max_it=50, divtol=1e4,
+              maxstep=1e8):
+    """SNESSolve_NEWTONLS with line search "none" (basic, full step), "bt" or "l2".  Returns (x, reason, its, hist)."""
     if linesearch in ("none", "basic"):
         return newton_ls_none(residual, jacobian, x0, rtol=rtol, atol=atol, stol=stol, max_it=max_it, divtol=divtol)
     x = x0.copy()
@@ -150,7 +151,10 @@ def newton_ls(residual, jacobian, x0, linesearch="none", rtol=1e-8, atol=1e-50, 
         y = spla.splu(J.tocsc()).solve(F)
         if not np.all(np.isfinite(y)):
             return x, DIVERGED_LINEAR_SOLVE, i, hist
-        xn, Fn, gnorm, lam, ok = linesearch_bt(residual, x, F, y, fnorm, J @ y)
+        if linesearch == "l2":
+            xn, Fn, gnorm, lam, ok = linesearch_l2(residual, x, y, fnorm, maxstep=maxstep)
+        else:
+            xn, Fn, gnorm, lam, ok = linesearch_bt(residual, x, F, y, fnorm, J @ y, maxstep=maxstep)
         if not ok:
             return x, DIVERGED_LINE_SEARCH, i, hist
         snorm = np.linalg.norm(xn - x)
@@ -160,3 +164,49 @@ def newton_ls(residual, jacobian, x0, linesearch="none", rtol=1e-8, atol=1e-50, 
         if reason:
             return x, reason, i + 1, hist
     return x, DIVERGED_MAX_IT, max_it, hist
+
+
+def linesearch_l2(residual, x, y, fnorm, lam0=1.0, maxstep=1e8, steptol=1e-12, max_it=1):
+    """PETSc's SNESLineSearchApply_L2 (secant search on ||F(x - lambda y)||^2; ``snes_linesearch_type l2`` of the
+    reference's examples 03, 07-10, e.g. fracture_dolfinx.py:132-138 with ``snes_linesearch_maxlambda 1``), restated
+    from memory of petsc/src/snes/linesearch/impls/l2/linesearchl2.c [3P-mem]: phi(lambda) = ||F(x - lambda y)||^2 is sampled at the ends and the midpoint of
+    [lambda_old, lambda]; one-sided second-order differences give phi' at both ends, their difference phi'' ; the
+    secant step lambda - phi'/|phi''| is taken (always downhill), reset to the midpoint when it falls below steptol,
+    abandoned when it is not finite or exceeds maxstep.  ``max_it`` = 1 is PETSc's default for l2.  A non-finite norm
+    halves the interval (and caps maxstep at 0.95 of the failed length).  Returns (x_new, F_new, gnorm, lambda, ok)."""
+    lam, lam_old = float(lam0), 0.0
+    phi_old = fnorm * fnorm
+    lam_mid = 0.5 * (lam + lam_old)
+    for _ in range(max_it):
+        while True:
+            with np.errstate(over="ignore", invalid="ignore"):
+                phi_mid = float(np.linalg.norm(residual(x - lam_mid * y))) ** 2
+                phi = float(np.linalg.norm(residual(x - lam * y))) ** 2
+            if np.isfinite(phi) and np.isfinite(phi_mid):
+                break
+            if lam <= steptol:
+                return x, None, np.nan, lam, False
+            maxstep = 0.95 * lam
+            lam = 0.5 * (lam + lam_old)
+            lam_mid = 0.5 * (lam + lam_old)
+        dl = lam - lam_old
+        dphi = (3.0 * phi - 4.0 * phi_mid + phi_old) / dl
+        dphi_old = (-3.0 * phi_old + 4.0 * phi_mid - phi) / dl
+        d2phi = (dphi - dphi_old) / dl
+        if d2phi > 0.0:
+            lam_new = lam - dphi / d2phi
+        elif d2phi < 0.0:
+            lam_new = lam + dphi / d2phi
+        else:
+            break
+        if lam_new < steptol:
+            lam_new = 0.5 * (lam + lam_old)
+        if not np.isfinite(lam_new) or lam_new > maxstep:
+            break
+        lam_old, lam, phi_old = lam, lam_new, phi
+        lam_mid = 0.5 * (lam + lam_old)
+    xn = x - lam * y
+    with np.errstate(over="ignore", invalid="ignore"):
+        Fn = residual(xn)
+    gnorm = float(np.linalg.norm(Fn))
+    return xn, Fn, gnorm, lam, bool(np.isfinite(gnorm))

@@ -15,6 +15,7 @@ E_INVALID, E_CUDA, E_CAPACITY, E_COMM, E_NOGPU = -1, -2, -3, -4, -5
 OBSTACLE_ARRAY, OBSTACLE_PHI_SET = 0, 1
 PC_JACOBI, PC_CHEBYSHEV, PC_MG = 0, 1, 2
 LINESEARCH_NONE, LINESEARCH_BT = 0, 1
+LINESEARCH_L2 = 2  # host loop only (linesearch.py); the library's own Newton loops know none and bt
 FORM_GRADIENT, FORM_MULTIPHASE, FORM_SIGNORINI = 1, 2, 3
 
 c_double_p = C.POINTER(C.c_double)

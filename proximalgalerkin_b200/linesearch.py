@@ -1,4 +1,4 @@
-"""SNES ``newtonls`` with PETSc's ``bt`` (cubic backtracking) line search for the obstacle engine.
+"""SNES ``newtonls`` with PETSc's ``bt`` (cubic backtracking) and ``l2`` (secant) line searches for the obstacle engine.
 
 The obstacle driver sets ``snes_linesearch_type none`` (examples/01_obstacle_problem/obstacle_pg.py:136)
 and that path runs entirely inside the library (``lvpp_newton_solve``).  The reference's other examples
@@ -131,11 +131,53 @@ def linesearch_bt(be, x, F, y, Jy, w, G, fnorm, alpha=1e-4, maxstep=1e8, steptol
     return gnorm, lam, False, ynorm
 
 
-class NewtonBT:
-    """SNESSolve_NEWTONLS with the bt line search, one step at a time (``begin`` then ``step`` until the
-    reason is non-zero) so that callers can time or log individual Newton steps."""
+def linesearch_l2(be, x, y, w, G, fnorm, lam0=1.0, maxstep=1e8, steptol=1e-12, max_it=1):
+    """SNESLineSearchApply_L2 on the step x - lambda y (``snes_linesearch_type l2``: the reference's examples 03 and
+    07-10, e.g. examples/03_fracture/fracture_dolfinx.py:132-138).  A secant iteration on
+    phi(lambda) = ||F(x - lambda y)||^2 from three samples of the bracket [lambda_old, lambda] (both ends and the
+    midpoint); PETSc's default is a single iteration.  On return ``w`` holds the new iterate and ``G`` its residual
+    (Jacobian assembled there).  Returns (gnorm, lambda, ok, ynorm)."""
+    ynorm = be.norm(y)
 
-    def __init__(self, be, rtol=1e-8, atol=1e-50, stol=1e-8, max_it=50, divtol=1e4):
+    def phi_at(lam):
+        be.waxpy(w, -lam, y, x)
+        g = be.residual(w, G)
+        return g * g
+
+    hi, lo = float(lam0), 0.0
+    p_lo = fnorm * fnorm
+    for _ in range(max_it):
+        mid = 0.5 * (hi + lo)
+        p_mid, p_hi = phi_at(mid), phi_at(hi)
+        while not (math.isfinite(p_mid) and math.isfinite(p_hi)):
+            if hi <= steptol:
+                return float("nan"), hi, False, ynorm
+            maxstep = 0.95 * hi  # never go back to a length where the function is not finite
+            hi = 0.5 * (hi + lo)
+            mid = 0.5 * (hi + lo)
+            p_mid, p_hi = phi_at(mid), phi_at(hi)
+        width = hi - lo
+        slope_hi = (3.0 * p_hi - 4.0 * p_mid + p_lo) / width     # one-sided second-order differences
+        slope_lo = (-3.0 * p_lo + 4.0 * p_mid - p_hi) / width
+        curv = (slope_hi - slope_lo) / width
+        if curv == 0.0:
+            break
+        cand = hi - slope_hi / abs(curv)                          # secant (Newton) step on phi', always downhill
+        if cand < steptol:
+            cand = 0.5 * (hi + lo)
+        if not math.isfinite(cand) or cand > maxstep:
+            break
+        lo, hi, p_lo = hi, cand, p_hi
+    gnorm = math.sqrt(phi_at(hi))
+    return gnorm, hi, math.isfinite(gnorm), ynorm
+
+
+class NewtonBT:
+    """SNESSolve_NEWTONLS with the bt (default) or l2 line search, one step at a time (``begin`` then ``step`` until
+    the reason is non-zero) so that callers can time or log individual Newton steps."""
+
+    def __init__(self, be, rtol=1e-8, atol=1e-50, stol=1e-8, max_it=50, divtol=1e4, linesearch="bt", maxstep=1e8):
+        self.linesearch, self.maxstep = linesearch, maxstep
         self.be = be
         self.rtol, self.atol, self.stol, self.max_it, self.divtol = rtol, atol, stol, max_it, divtol
         self.F, self.y, self.Jy, self.w, self.G = (be.vector() for _ in range(5))
@@ -164,7 +206,10 @@ class NewtonBT:
         if kreason < 0:
             self.reason = DIVERGED_LINEAR_SOLVE
             return self.reason
-        gnorm, lam, ok, ynorm = linesearch_bt(be, x, self.F, self.y, self.Jy, self.w, self.G, self.fnorm)
+        if self.linesearch == "l2":
+            gnorm, lam, ok, ynorm = linesearch_l2(be, x, self.y, self.w, self.G, self.fnorm, maxstep=self.maxstep)
+        else:
+            gnorm, lam, ok, ynorm = linesearch_bt(be, x, self.F, self.y, self.Jy, self.w, self.G, self.fnorm, maxstep=self.maxstep)
         self.last_lambda = lam
         if not ok:
             # the Jacobian now sits at the last trial point: restore it at x for a caller that carries on

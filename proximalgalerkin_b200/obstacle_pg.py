@@ -175,7 +175,9 @@ class LvppStepper:
 
             o = self.opts
             self.nb = linesearch.NewtonBT(linesearch.DeviceBackend(dev, o), rtol=o.snes_rtol, atol=o.snes_atol,
-                                          stol=o.snes_stol, max_it=o.snes_max_it, divtol=o.snes_divtol)
+                                          stol=o.snes_stol, max_it=o.snes_max_it, divtol=o.snes_divtol,
+                                          linesearch="l2" if o.snes_linesearch == 2 else "bt",
+                                          maxstep=getattr(o, "linesearch_maxstep", 1e8))
         self._begin_outer()
 
     def _begin_outer(self):

@@ -351,8 +351,13 @@ def newton_options(options, generic=False):
         # mixed-form engine: inside the library (forms.cu); obstacle engine: the host loop of linesearch.py over
         # the library's assembly / Krylov / J*v entry points
         o.snes_linesearch = _capi.LINESEARCH_BT
+    elif ls == "l2" and not generic:
+        # PETSc's secant line search (the reference's examples 03, 07-10): obstacle engine only, host loop of linesearch.py
+        o.snes_linesearch = _capi.LINESEARCH_L2
     else:
         raise NotImplementedError(f"snes_linesearch_type {ls!r}")
+    # snes_linesearch_maxlambda (PETSc >= 3.23; fracture_dolfinx.py:135) / snes_linesearch_maxstep (older name)
+    o.linesearch_maxstep = float(opts.get("snes_linesearch_maxlambda", opts.get("snes_linesearch_maxstep", 1e8)))
     if opts.get("ksp_gmres_restart") is not None:
         o.ksp_restart = int(opts["ksp_gmres_restart"])
     st = opts.get("snes_type", "newtonls")
@@ -475,13 +480,15 @@ class SNESSolver:
         dev = self.problem.device_problem
         dev.sync_coefficients()
         xh = self.problem.u.x.array
-        if self._opts.snes_linesearch == _capi.LINESEARCH_BT:
+        if self._opts.snes_linesearch in (_capi.LINESEARCH_BT, _capi.LINESEARCH_L2):
             from . import linesearch
 
             o = self._opts
             dev.x.set(xh)
             nb = linesearch.NewtonBT(linesearch.DeviceBackend(dev, o), rtol=o.snes_rtol, atol=o.snes_atol, stol=o.snes_stol,
-                                     max_it=o.snes_max_it, divtol=o.snes_divtol)
+                                     max_it=o.snes_max_it, divtol=o.snes_divtol,
+                                     linesearch="l2" if o.snes_linesearch == _capi.LINESEARCH_L2 else "bt",
+                                     maxstep=getattr(o, "linesearch_maxstep", 1e8))
             reason, its = nb.solve(dev.x)
             fnorm, lin = nb.fnorm, nb.linear_its
             if reason > 0:  # SNESSolver.solve only overwrites the caller's function on convergence (problem.py:121-123)

@@ -45,6 +45,33 @@ def test_obstacle_bt_matches_oracle(lib):
     assert np.linalg.norm(X.numpy() - xo) <= 1e-8 * np.linalg.norm(xo)
 
 
+def test_obstacle_l2_matches_oracle(lib):
+    """snes_linesearch_type l2 (+ snes_linesearch_maxlambda 1, the setting of fracture_dolfinx.py:132-138) through
+    NonlinearProblem.solve() against the restated PETSc loop."""
+    import proximalgalerkin_b200 as lvpp
+    from oracle import mesh as omesh
+    from oracle import obstacle as oobs
+    from oracle import snes as osnes
+
+    n, alpha = 6, 3.0
+    msh = lvpp.mesh.create_box(n, n, n)
+    s = lvpp.obstacle_pg.setup(msh, 1, petsc_options={"ksp_type": "gmres", "pc_type": "mg", "ksp_rtol": 1e-12, "snes_rtol": 1e-10,
+                                                       "snes_max_it": 80, "snes_linesearch_type": "l2", "snes_linesearch_maxlambda": 1})
+    orc = oobs.ObstacleOracle(omesh.box_kuhn(n, n, n))
+    rng = np.random.default_rng(2)
+    xk = 0.3 * rng.standard_normal(orc.num_rows)
+    x0 = np.zeros(orc.num_rows)
+    x0[1::2] = -2.0
+    xo, reason_o, its_o, _ = osnes.newton_ls(lambda z: orc.assemble_residual(z, xk, alpha), lambda z: orc.jacobian(z, alpha),
+                                             x0, linesearch="l2", rtol=1e-10, max_it=80, maxstep=1.0)
+    s["alpha"].value = alpha
+    s["sol_k"].x.array[:] = xk
+    s["sol"].x.array[:] = x0
+    s["problem"].solve()
+    assert (s["problem"].solver.getConvergedReason(), s["problem"].solver.getIterationNumber()) == (reason_o, its_o)
+    assert np.linalg.norm(s["sol"].x.array - xo) <= 1e-8 * np.linalg.norm(xo)
+
+
 def test_nonlinear_problem_bt_option(lib):
     """The option routes NonlinearProblem.solve() through the same loop; from the zero start of the LVPP iteration
     the full step is always accepted, so bt reproduces the line-search-free Newton counts."""
