@@ -70,4 +70,10 @@ def test_mg_precision_quantisers_and_pair_layout():
         L.J, L.Binv = J, B
     y, its_bf16 = mp.gmres_right(J0, lambda v: mg.cycle(v, 0, 1), rhs)
     assert its_bf16 <= its_exact + 4  # (this late state moves by +-2 with any perturbation of the cycle: fp32 records give 16)
+    # single-precision vectors inside the cycle need the flexible variant: plain right-preconditioned GMRES degrades
+    prec32 = lambda v: mq.q_fp32(mq.cycle32(mg, mq.q_fp32(v)))  # noqa: E731
+    yf, its_fg = mq.fgmres(J0, prec32, rhs)
+    _, its_plain = mp.gmres_right(J0, prec32, rhs)
+    assert its_fg <= its_exact + 5 and its_plain > its_fg
+    assert np.linalg.norm(J0 @ yf - rhs) <= 1e-10 * np.linalg.norm(rhs)
     assert np.linalg.norm(J0 @ y - rhs) <= 1e-10 * np.linalg.norm(rhs)

@@ -70,7 +70,7 @@ def main():
     ap.add_argument("--outer", type=int, default=4)
     ap.add_argument("--cheb", type=float, default=6.0)
     ap.add_argument("--formats", default="fp64,fp32,bf16,bf16+v32,fp16",
-                    help="comma list; +v32 also rounds the cycle's vectors to fp32, +b32 only the block inverses")
+                    help="comma list; +v32 also rounds the cycle's vectors to fp32, +b32 only the block inverses, +fg uses flexible GMRES")
     args = ap.parse_args()
     n = args.size
     orc = oobs.ObstacleOracle(omesh.box_kuhn(n, n, n) if args.dim == 3 else omesh.rectangle(n, n))
@@ -94,13 +94,60 @@ def main():
                 prec = lambda v: q_fp32(cycle32(mg, q_fp32(v)))  # noqa: E731
             else:
                 prec = lambda v: mg.cycle(v, 0, 1)  # noqa: E731
-            _, its = mp.gmres_right(J0, prec, rhs)
+            _, its = (fgmres if "fg" in mods else mp.gmres_right)(J0, prec, rhs)
             for L, (J, B) in zip(mg.levels, exact):
                 L.J, L.Binv = J, B
             totals[fmt] += its
             line += f" {fmt} {its}"
         print(line, flush=True)
     print("# total Krylov iterations: " + ", ".join(f"{f} {t}" for f, t in totals.items()))
+
+
+def fgmres(J, prec, b, rtol=1e-12, restart=50, maxit=400):
+    """Flexible GMRES (Saad): keeps Z_j = prec(V_j), so the preconditioner may change from one application to the
+    next -- e.g. a cycle whose vectors are rounded to single precision.  Returns (y, iterations)."""
+    n = b.size
+    y = np.zeros(n)
+    bnorm = np.linalg.norm(b)
+    total = 0
+    while total < maxit:
+        r = b - J @ y
+        beta = np.linalg.norm(r)
+        if beta <= rtol * bnorm:
+            return y, total
+        V = np.zeros((restart + 1, n))
+        Z = np.zeros((restart, n))
+        H = np.zeros((restart + 1, restart))
+        V[0] = r / beta
+        g = np.zeros(restart + 1)
+        g[0] = beta
+        cs, sn = np.zeros(restart), np.zeros(restart)
+        k = 0
+        for j in range(restart):
+            Z[j] = prec(V[j])
+            w = J @ Z[j]
+            for i in range(j + 1):
+                H[i, j] = V[i] @ w
+                w -= H[i, j] * V[i]
+            H[j + 1, j] = np.linalg.norm(w)
+            if H[j + 1, j] > 0:
+                V[j + 1] = w / H[j + 1, j]
+            for i in range(j):
+                t = cs[i] * H[i, j] + sn[i] * H[i + 1, j]
+                H[i + 1, j] = -sn[i] * H[i, j] + cs[i] * H[i + 1, j]
+                H[i, j] = t
+            den = np.hypot(H[j, j], H[j + 1, j])
+            cs[j], sn[j] = H[j, j] / den, H[j + 1, j] / den
+            H[j, j], H[j + 1, j] = den, 0.0
+            g[j + 1] = -sn[j] * g[j]
+            g[j] = cs[j] * g[j]
+            total += 1
+            k = j + 1
+            if abs(g[j + 1]) <= rtol * bnorm or total >= maxit:
+                break
+        c = np.linalg.solve(np.triu(H[:k, :k]), g[:k])
+        y = y + Z[:k].T @ c
+    return y, total
 
 
 def cycle32(mg, b, l=0):
