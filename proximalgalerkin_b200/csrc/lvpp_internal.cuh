@@ -214,6 +214,8 @@ struct lvpp_problem {
   int32_t* coarse_gmap = nullptr; // [V coarsest] global coarse node of every local node
   double* coarse_bg = nullptr;    // [coarse_n] gathered right-hand side
   double* gm_V = nullptr;         // GMRES basis [(restart + 1) * 2V]
+  bool gm_flexible = false;       // experimental (LVPP_GMRES_FLEXIBLE=1): FGMRES, keeps Z_j = M^-1 V_j
+  double* gm_Z = nullptr;         // [restart * 2V] when gm_flexible
   int gm_restart = 0;
   // classical Gram-Schmidt is repeated when less than eta2 of ||w||^2 survives the projection (Daniel et al.)
   double gm_eta2 = 0.01;         // (0.5 = Daniel's criterion; PETSc's default never repeats; profiles/r01_mg_scan.txt)

@@ -682,6 +682,11 @@ int lvpp_mg_setup(lvpp_problem* h) {
   h->gm_restart = (int)env_double("LVPP_GMRES_RESTART", 50);
   if (h->gm_restart < 2 || h->gm_restart > 200) { lvpp_set_error("bad LVPP_GMRES_RESTART"); return LVPP_E_INVALID; }
   CKR(lvpp_dalloc(h, &h->gm_V, (size_t)(h->gm_restart + 1) * 2 * h->V));
+  // Flexible GMRES (experimental, off by default): the preconditioned vectors Z_j = M^-1 V_j are kept, the update is
+  // y += Z c instead of y += M^-1 (V c) -- one cycle less per restart, and the cycle may then differ from one
+  // application to the next (a cycle with single-precision vectors: tools/mg_precision.py +fg)
+  h->gm_flexible = env_double("LVPP_GMRES_FLEXIBLE", 0.0) != 0.0;
+  if (h->gm_flexible) CKR(lvpp_dalloc(h, &h->gm_Z, (size_t)h->gm_restart * 2 * h->V));
   CKR(lvpp_dalloc(h, &h->gm_h, (size_t)h->gm_restart + 72));
   CKR(lvpp_dalloc(h, &h->gm_part, (size_t)(h->gm_restart + 2) * h->npartials));
   CK(cudaMallocHost((void**)&h->gm_h_host, sizeof(double) * (h->gm_restart + 72)));
@@ -1126,6 +1131,8 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
       h->smooth_sample_recorded = false;
       CKR(lvpp_mg_vcycle(h, vec(j), &z));
       h->smooth_sample_pending = false;
+      if (h->gm_Z)  // FGMRES: keep Z_j (owned entries; y's ghosts are refreshed by the next residual)
+        CK(cudaMemcpyAsync(h->gm_Z + (size_t)j * 2 * stride2, z, sizeof(double) * 2 * Vown, cudaMemcpyDeviceToDevice, h->stream));
       if (h->nranks > 1) CKR(lvpp_halo_forward_level(h, h->halo, z));
       CK(cudaEventRecord(h->evs0, h->stream));
       CKR(level_op_local(h, L0, EPI_NONE, 1.0, z, nullptr, vec(j + 1)));
@@ -1215,11 +1222,17 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
     CK(cudaMemcpyAsync(h->gm_h, h->gm_h_host, sizeof(double) * k, cudaMemcpyHostToDevice, h->stream));
     // the combination goes to v_m (free: k <= m columns use v_0..v_{k-1}; v_k holds w and is dead)
     double* comb = vec(k);
-    LAUNCH(h, k_lincomb, nb, 256, 0, Vown, Vb, stride2, k, h->gm_h, (double2*)comb);
-    CK(cudaGetLastError());
-    double* z = nullptr;
-    CKR(lvpp_mg_vcycle(h, comb, &z));
-    LAUNCH(h, k_axpby, nb, 256, 0, Vown, 1.0, (const double2*)z, 1, (double2*)d_y);
+    if (h->gm_Z) {  // FGMRES: y += Z yv
+      LAUNCH(h, k_lincomb, nb, 256, 0, Vown, (const double2*)h->gm_Z, stride2, k, h->gm_h, (double2*)comb);
+      CK(cudaGetLastError());
+      LAUNCH(h, k_axpby, nb, 256, 0, Vown, 1.0, (const double2*)comb, 1, (double2*)d_y);
+    } else {
+      LAUNCH(h, k_lincomb, nb, 256, 0, Vown, Vb, stride2, k, h->gm_h, (double2*)comb);
+      CK(cudaGetLastError());
+      double* z = nullptr;
+      CKR(lvpp_mg_vcycle(h, comb, &z));
+      LAUNCH(h, k_axpby, nb, 256, 0, Vown, 1.0, (const double2*)z, 1, (double2*)d_y);
+    }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));  // gm_h_host is reused by the next cycle
   }

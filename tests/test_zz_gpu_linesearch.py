@@ -123,10 +123,11 @@ def test_residual_and_jacobian_at_extreme_latent_values(lib):
 
 
 @pytest.mark.parametrize("env", [{"LVPP_GMRES_WEIGHT": "auto"}, {"LVPP_GMRES_FUSED_NORM": "1"},
-                                 {"LVPP_GMRES_WEIGHT": "auto", "LVPP_GMRES_FUSED_NORM": "1"}])
+                                 {"LVPP_GMRES_WEIGHT": "auto", "LVPP_GMRES_FUSED_NORM": "1"},
+                                 {"LVPP_GMRES_FLEXIBLE": "1"}, {"LVPP_GMRES_FLEXIBLE": "1", "LVPP_GMRES_WEIGHT": "auto"}])
 def test_experimental_gmres_switches_solve_the_same_system(lib, env, monkeypatch):
-    """The equilibrated residual norm and the one-reduction Gram-Schmidt (both off by default) change the Krylov
-    process, not the solution."""
+    """The equilibrated residual norm, the one-reduction Gram-Schmidt and flexible GMRES (all off by default) change
+    the Krylov process, not the solution."""
     _solve_with_env(env, monkeypatch)
 
 

@@ -8,7 +8,7 @@ python bench.py > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err; tail -1 g
 echo "== experimental: one reduction per GMRES iteration"
 tools/mg_scan.sh "LVPP_GMRES_FUSED_NORM=0" "LVPP_GMRES_FUSED_NORM=1" "LVPP_GMRES_WEIGHT=auto" "LVPP_GMRES_WEIGHT=auto LVPP_MG_CHEB=10" "LVPP_MG_CHEB=10" "LVPP_MG_CHEB=0"
 echo "== experimental: bf16 pair records in the cycle (10 instead of 16 bytes per slot; tools/mg_precision.py: same iteration counts)"
-tools/mg_scan.sh "LVPP_MG_PACK=bf16" "LVPP_MG_PACK=bf16 LVPP_MG_UNROLL=8" "LVPP_MG_PACK=bf16 LVPP_GMRES_WEIGHT=auto"
+tools/mg_scan.sh "LVPP_MG_PACK=bf16" "LVPP_MG_PACK=bf16 LVPP_MG_UNROLL=8" "LVPP_MG_PACK=bf16 LVPP_GMRES_WEIGHT=auto" "LVPP_GMRES_FLEXIBLE=1" "LVPP_GMRES_FLEXIBLE=1 LVPP_MG_PACK=bf16 LVPP_GMRES_WEIGHT=auto"
 export LVPP_GMRES_WEIGHT=auto   # the equilibrated residual norm: 17-26 Krylov iterations through the whole 64^3 CPU emulation
 for cfg in "--linesearch none" "--linesearch bt" "--linesearch none --snes-rtol 1e-9" "--linesearch bt --snes-rtol 1e-9"; do
   tag=$(echo "$cfg" | tr -d ' -' )
