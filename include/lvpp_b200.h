@@ -121,6 +121,10 @@ typedef struct lvpp_newton_opts {
 
 #define LVPP_LINESEARCH_NONE 0
 #define LVPP_LINESEARCH_BT 1
+/* 2 = PETSc's "l2" (examples/03_fracture/fracture_dolfinx.py:132-138): carried in the options for the obstacle engine's
+   host loop (proximalgalerkin_b200/linesearch.py over lvpp_assemble_residual / lvpp_linear_solve); the library's own
+   Newton loops read it as "none" */
+#define LVPP_LINESEARCH_L2 2
 #define LVPP_SNES_DIVERGED_LINE_SEARCH (-6)
 
 typedef struct lvpp_stats {
