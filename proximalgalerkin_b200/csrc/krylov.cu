@@ -6,6 +6,8 @@
 // (smoothed) diagonal for the (0,0) block and the diagonal of D + M diag(alpha K)^-1 M for the Schur
 // complement.  All recurrence scalars live on the device (KryScal); the host only polls a
 // convergence flag every few iterations, so an iteration is five back-to-back launches.
+#include <cstring>
+
 #include "lvpp_internal.cuh"
 
 // pinv_u = 1 / (alpha K_ii)  (1 on Dirichlet rows);  pinv_psi = 1 / (D_ii + M_ii^2 / (alpha K_ii))
@@ -233,6 +235,14 @@ int lvpp_solve_linear(lvpp_problem* h, const double* d_rhs, double* d_y, const l
       // the Chebyshev sweeps amplify eigenvalues above their interval: a diverged / stagnated solve is retried once
       // with eigenvalue estimates redone from scratch
       int32_t its2 = 0;
+      // ... and in the equilibrated residual norm (multigrid.cu:lvpp_gmres_mg), from here on: every stagnating solve of
+      // the CPU emulation of whole LVPP solves converges in 17 - 40 iterations with it.  The default
+      // path is untouched: this only runs after a solve has already failed.  LVPP_GMRES_WEIGHT=off forbids it.
+      const char* gw = getenv("LVPP_GMRES_WEIGHT");
+      if (!(gw && strcmp(gw, "off") == 0) && !h->gm_weight_auto) {
+        h->gm_weight_auto = true;
+        if (getenv("LVPP_MG_VERBOSE") && h->rank == 0) fprintf(stderr, "[lvpp mg] Krylov solve failed: equilibrated residual norm from here on\n");
+      }
       CKR(lvpp_mg_reestimate(h));
       CKR(lvpp_gmres_mg(h, d_rhs, d_y, o, &its2, &reason1, rnorm));
       its1 += its2;
