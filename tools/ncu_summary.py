@@ -20,7 +20,7 @@ def main(path):
         unit = r.get("Metric Unit", "ns")
         us = val / 1e3 if unit in ("ns", "nsecond") else val if unit in ("us", "usecond") else val * 1e3
         name = re.sub(r"\(.*", "", r["Kernel Name"]).strip()
-        if "k_block_op" in name:  # the same kernel runs on every multigrid level: split fine / coarse by grid
+        if "k_block_op" in name or "k_packed" in name:  # the same kernel runs on every multigrid level: split fine / coarse by grid
             name += " fine" if int(r["Grid Size"].strip("()").split(",")[0]) >= 148 * 6 else " coarse"
         agg[name][0] += 1
         agg[name][1] += us
