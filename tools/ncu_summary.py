@@ -21,7 +21,9 @@ def main(path):
         us = val / 1e3 if unit in ("ns", "nsecond") else val if unit in ("us", "usecond") else val * 1e3
         name = re.sub(r"\(.*", "", r["Kernel Name"]).strip()
         if "k_block_op" in name or "k_packed" in name:  # the same kernel runs on every multigrid level: split fine / coarse by grid
-            name += " fine" if int(r["Grid Size"].strip("()").split(",")[0]) >= 148 * 6 else " coarse"
+            # ("fine" = the grid is at its cap of 148 x blocks per SM: levels 0 and 1 at n = 215)
+            cap = 148 * (3 if "k_packed" in name else 6)
+            name += " fine" if int(r["Grid Size"].strip("()").split(",")[0]) >= cap else " coarse"
         agg[name][0] += 1
         agg[name][1] += us
     tot = sum(v[1] for v in agg.values())
