@@ -368,7 +368,8 @@ def run_b200(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"3-D P1 obstacle LVPP (configs[1]): {nxy}x{nxy}x{nz} cubes x 6 tets, "
                                    f"{rows_global} rows, {stats0['nnz']} nnz/GPU (CSR-equivalent)",
-                       "n": n, "rows": rows_global, "alpha_scheme": "double_exponential", "alpha_max": 1e2,
+                       "n": n, "rows": rows_global, "primal_dofs": rows_global // 2,  # the reference's CSV column "dofs" (obstacle_pg.py:237,255)
+                       "alpha_scheme": "double_exponential", "alpha_max": 1e2,
                        "snes_rtol": 1e-6, "ksp": ("MINRES + block-Jacobi/Schur-diag" if args.pc == "jacobi" else
                                "GMRES(50) + monolithic aggregation multigrid V(2,2) (node-block Jacobi sweeps with Chebyshev-root "
                                "dampings, ratio 6; packed single-precision cycle operator, fp64 Krylov operator)"), "ksp_rtol": args.ksp_rtol,
