@@ -77,3 +77,24 @@ def test_mg_precision_quantisers_and_pair_layout():
     assert its_fg <= its_exact + 5 and its_plain > its_fg
     assert np.linalg.norm(J0 @ yf - rhs) <= 1e-10 * np.linalg.norm(rhs)
     assert np.linalg.norm(J0 @ y - rhs) <= 1e-10 * np.linalg.norm(rhs)
+
+
+def test_full_solve_cpu_tool_runs_a_whole_lvpp_solve(capsys, monkeypatch):
+    """tools/full_solve_cpu.py (the whole LVPP solve with the prototype's multigrid GMRES as linear solver): Newton
+    counts of the oracle's exact-LU solve on a small mesh, with the Euclidean and the equilibrated residual norm."""
+    import sys
+
+    from oracle import lvpp_driver
+    from oracle import mesh as omesh
+    from oracle import obstacle as oobs
+
+    orc = oobs.ObstacleOracle(omesh.box_kuhn(6, 6, 6))
+    _, h = lvpp_driver.solve_obstacle(orc, 500, "double_exponential", 1e2, 1e-4)
+    for extra in ([], ["--equilibrate"]):
+        fs = _load("full_solve_cpu")
+        monkeypatch.setattr(sys, "argv", ["full_solve_cpu.py", "--size", "6"] + extra)
+        fs.main()
+        out = capsys.readouterr().out
+        assert "converged" in out and "diverged" not in out
+        counts = [int(ln.split(":")[1].split()[0]) for ln in out.splitlines() if ln.startswith("== outer")]
+        assert counts == h["newton_steps"], (extra, counts, h["newton_steps"])
