@@ -383,6 +383,7 @@ def run_b200(args):
             "mg_levels": s1["mg_levels"], "wall_s": wall, "setup_s": t_setup,
             "roofline": roofline, "roofline_jv": roof_extra, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "assembly": asm, "device_bytes": stats0["device_bytes"], "outer_history": st.history,
+            "env": {k: v for k, v in sorted(os.environ.items()) if k.startswith("LVPP_")},  # experimental switches in force
         }
         print(json.dumps(line))
     if world > 1:
