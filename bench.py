@@ -97,6 +97,8 @@ def cpu_newton_steps(n_cpu, steps, warmup):
     from oracle import lvpp_driver, mesh as omesh, obstacle as oobs, snes as osnes
 
     orc = oobs.ObstacleOracle(omesh.box_kuhn(n_cpu, n_cpu, n_cpu))
+    import scipy.sparse.linalg as spla
+
     x = np.zeros(orc.num_rows)
     xk = x.copy()
     alpha_k, alpha, k = 1, 1.0, 0
@@ -111,8 +113,6 @@ def cpu_newton_steps(n_cpu, steps, warmup):
         while done < total:
             if done == warmup and t0 is None:
                 t0 = time.perf_counter()
-            import scipy.sparse.linalg as spla
-
             y = spla.splu(orc.jacobian(x, alpha).tocsc()).solve(F)
             x = x - y
             F = orc.assemble_residual(x, xk, alpha)
@@ -122,8 +122,11 @@ def cpu_newton_steps(n_cpu, steps, warmup):
             if osnes.converged_default(it, np.linalg.norm(x), np.linalg.norm(y), fnorm, fnorm0 * 1e-6, fnorm0, 1e-50, 1e-8, 1e4):
                 break
         obs = orc.observables(x, xk, alpha)
-        if np.sqrt(obs[4]) < 1e-4:
-            break
+        if np.sqrt(obs[4]) < 1e-4:  # solve finished: the next step starts a fresh solve, as on the GPU arm
+            x = np.zeros(orc.num_rows)
+            xk = x.copy()
+            alpha_k, alpha, k = 1, 1.0, 0
+            continue
         xk = x.copy()
         k += 1
     t_timed = time.perf_counter() - t0 if t0 is not None else float("nan")
@@ -216,10 +219,27 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # A step never raises out of the timed region and the region always holds exactly K steps: when the LVPP solve
+    # finishes (about 20 Newton steps at the CI parameters) or a Newton solve fails, the next step starts a fresh solve
+    # from the zero iterate on the same handle (LvppStepper.reset: zero x and x_k, alpha schedule from k = 0, residual +
+    # Jacobian at the zero iterate -- all inside the timed region).
+    solves, failures = [], []
+
+    def advance():
+        try:
+            alive = st.step()
+        except lvpp.NotConvergedError as e:
+            failures.append({"solve": len(solves), "outer": st.k, "newton": st.newton_its, "reason": e.reason})
+            alive = False
+        if not alive:
+            solves.append({"newton_steps": list(st.history["newton_steps"]), "krylov_iterations": list(st.history["krylov_iterations"]),
+                           "alpha": list(st.history["alpha"]), "primal_increment": list(st.history["primal_increment"]),
+                           "converged": bool(st.finished)})
+            st.reset()
+
     # ---- warm-up: the first W Newton steps of the solve
     for _ in range(args.warmup):
-        if not st.step():
-            break
+        advance()
     # ---- timed region: exactly K Newton steps
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -230,10 +250,8 @@ def run_b200(args):
     t0 = time.perf_counter()
     done = 0
     while done < args.steps:
-        alive = st.step()
+        advance()
         done += 1
-        if not alive:
-            break
     dev_ms = dev.timer_stop()
     barrier()
     wall = time.perf_counter() - t0
@@ -314,15 +332,25 @@ def run_b200(args):
         n_solves = 0
         barrier()
         te = time.perf_counter()
+        e2e_fail = []
         while steps_e2e < args.steps:
             alpha.value, alpha_k = lvpp.obstacle_pg.alpha_update("double_exponential", k, alpha.value, alpha_k, 1e2)
-            problem.solve()
-            steps_e2e += problem.solver.getIterationNumber()
+            ok = True
+            try:
+                problem.solve()
+            except lvpp.NotConvergedError as e:
+                e2e_fail.append({"outer": k, "reason": e.reason})
+                ok = False
+            steps_e2e += max(problem.solver.getIterationNumber(), 1)
             n_solves += 1
-            dev.x.set(sol.x.array)
-            obs = dev.observables(dev.x)
-            if np.sqrt(obs[4]) < 1e-4:
-                break
+            if ok:
+                dev.x.set(sol.x.array)
+                obs = dev.observables(dev.x)
+            if not ok or np.sqrt(obs[4]) < 1e-4:  # solve finished (or failed): the next proximal step starts a fresh solve
+                sol.x.array[:] = 0.0
+                sol_k.x.array[:] = 0.0
+                alpha.value, alpha_k, k = 1.0, 1, 0
+                continue
             sol_k.x.array[:] = sol.x.array[:]
             k += 1
         barrier()
@@ -336,7 +364,7 @@ def run_b200(args):
             "value": rows_global * steps_e2e / te, "unit": UNIT, "steps": steps_e2e, "seconds": te,
             "h2d_bytes_per_step": 3 * vec_bytes * n_solves / max(steps_e2e, 1),  # sol, sol_k (+ sol for observables)
             "d2h_bytes_per_step": vec_bytes * n_solves / max(steps_e2e, 1),
-            "api": "NonlinearProblem.solve() per proximal step, host numpy buffers",
+            "api": "NonlinearProblem.solve() per proximal step, host numpy buffers", "failures": e2e_fail,
         }
 
     # ---- assembly kernels (reported, not the headline)
@@ -382,7 +410,8 @@ def run_b200(args):
             "newton_steps_per_sec": done / secs, "krylov_iterations": kry, "vcycles": s1["vcycles"] - s0["vcycles"],
             "mg_levels": s1["mg_levels"], "wall_s": wall, "setup_s": t_setup,
             "roofline": roofline, "roofline_jv": roof_extra, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "assembly": asm, "device_bytes": stats0["device_bytes"], "outer_history": st.history,
+            "assembly": asm, "device_bytes": stats0["device_bytes"],
+            "solves_completed": solves, "solve_in_progress": {k: list(v) for k, v in st.history.items()}, "failures": failures,
             "env": {k: v for k, v in sorted(os.environ.items()) if k.startswith("LVPP_")},  # experimental switches in force
         }
         print(json.dumps(line))

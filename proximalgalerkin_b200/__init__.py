@@ -11,6 +11,7 @@ from .problem import (
     DeviceProblem,
     DeviceVector,
     NonlinearProblem,
+    NotConvergedError,
     SNESProblem,
     SNESSolver,
     derivative,
@@ -22,6 +23,7 @@ __all__ = [
     "SNESProblem",
     "SNESSolver",
     "NonlinearProblem",
+    "NotConvergedError",
     "DeviceProblem",
     "DeviceVector",
     "DeviceMatrix",

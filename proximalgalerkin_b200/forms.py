@@ -226,5 +226,7 @@ class FormNonlinearProblem:
         self.x[:] = self.X.numpy()
         err = self.options.get("snes_error_if_not_converged", False)
         if reason <= 0 and (err is None or err):
-            raise RuntimeError(f"SNES did not converge: reason {reason} after {its} iterations")
+            from .problem import NotConvergedError
+
+            raise NotConvergedError(f"SNES did not converge: reason {reason} after {its} iterations", reason, its)
         return self.x

@@ -9,7 +9,7 @@ of the XDMF file name.  ``LvppStepper`` runs the same loop device-resident, one 
 import numpy as np
 
 from . import fem, recovery
-from .problem import NonlinearProblem, derivative, newton_options, obstacle_residual, DeviceVector
+from .problem import NonlinearProblem, NotConvergedError, derivative, newton_options, obstacle_residual, DeviceVector
 
 
 def alpha_update(rule, k, alpha_value, alpha_k, alpha_max, C=1.0, r=1.5, q=1.5):
@@ -97,8 +97,8 @@ def solve_problem(msh, polynomial_order=1, maximum_number_of_outer_loop_iteratio
             alpha.value = ctl.alpha
             try:
                 problem.solve()
-            except RuntimeError:  # *_error_if_not_converged: the reason is on the solver either way
-                pass
+            except NotConvergedError:  # *_error_if_not_converged: the reason is on the solver either way
+                pass  # (a device / communication failure is an LvppError and propagates)
         reason = problem.solver.getConvergedReason()
         n = problem.solver.getIterationNumber()
         if ctl is not None:
@@ -156,19 +156,10 @@ class LvppStepper:
         dev = self.dev
         self.x = dev.x
         self.xk = DeviceVector(dev.n, dev.device)
-        self.x.tensor.zero_()
-        self.xk.tensor.zero_()
-        self.k = 0  # outer iteration
-        self.alpha_value, self.alpha_k = 1.0, 1
-        self.newton_its = 0  # within the current outer iteration
         self.total_newton = 0
         self.total_krylov = 0
-        self.finished = False
-        self.history = {k: [] for k in ("newton_steps", "alpha", "primal_increment", "reason")}
-        # alpha_scheme "adaptive": failure-recovering control of fracture_dolfinx.py:215-283 (recovery.py)
-        self.ctl = recovery.AdaptiveAlpha(alpha_max=alpha_max, **(adaptive or {})) if alpha_scheme == "adaptive" else None
-        if self.ctl is not None:
-            self.history["attempts"] = self.ctl.attempts
+        self.solves_completed = 0
+        self._adaptive = adaptive
         self.nb, self.last_lambda = None, 1.0
         if self.opts.snes_linesearch != 0:
             from . import linesearch
@@ -178,6 +169,24 @@ class LvppStepper:
                                           stol=o.snes_stol, max_it=o.snes_max_it, divtol=o.snes_divtol,
                                           linesearch="l2" if o.snes_linesearch == 2 else "bt",
                                           maxstep=getattr(o, "linesearch_maxstep", 1e8))
+        self.reset()
+
+    def reset(self):
+        """Start a fresh LVPP solve from the zero iterate (obstacle_pg.py:157-158) on the same handle: bench.py times
+        K Newton steps whatever K is, so a solve that finishes inside the timed region is followed by the next one."""
+        self.x.tensor.zero_()
+        self.xk.tensor.zero_()
+        self.k = 0  # outer iteration
+        self.alpha_value, self.alpha_k = 1.0, 1
+        self.newton_its = 0  # within the current outer iteration
+        self.krylov_outer = 0  # Krylov iterations within the current outer iteration
+        self.finished = False
+        self.history = {k: [] for k in ("newton_steps", "alpha", "primal_increment", "reason", "krylov_iterations")}
+        # alpha_scheme "adaptive": failure-recovering control of fracture_dolfinx.py:215-283 (recovery.py, SURVEY 8f N2)
+        self.ctl = (recovery.AdaptiveAlpha(alpha_max=self.alpha_max, **(self._adaptive or {}))
+                    if self.alpha_scheme == "adaptive" else None)
+        if self.ctl is not None:
+            self.history["attempts"] = self.ctl.attempts
         self._begin_outer()
 
     def _begin_outer(self):
@@ -193,6 +202,7 @@ class LvppStepper:
             self.fnorm0 = self.dev.newton_begin(self.x)
         self.ttol = self.fnorm0 * self.opts.snes_rtol
         self.newton_its = 0
+        self.krylov_outer = 0
 
     def _snes_reason(self, it, xnorm, snorm, fnorm):
         o = self.opts
@@ -221,11 +231,13 @@ class LvppStepper:
             self.newton_its = self.nb.its
             self.total_newton += 1
             self.total_krylov += self.nb.linear_its - lin0
+            self.krylov_outer += self.nb.linear_its - lin0
         else:
             (fnorm, ynorm, xnorm), kits, kreason = self.dev.newton_step(self.x, self.opts)
             self.newton_its += 1
             self.total_newton += 1
             self.total_krylov += kits
+            self.krylov_outer += kits
             reason = -3 if kreason < 0 else self._snes_reason(self.newton_its, xnorm, ynorm, fnorm)
             if reason == 0 and self.newton_its >= self.opts.snes_max_it:
                 reason = -5
@@ -245,16 +257,18 @@ class LvppStepper:
                 self._begin_outer()
                 return True
         if reason < 0:
-            raise RuntimeError(f"SNES did not converge: reason {reason}")
+            raise NotConvergedError(f"SNES did not converge: reason {reason}", reason, self.newton_its)
         obs = self.dev.observables(self.x)
         increment = float(np.sqrt(obs[4]))
         self.history["newton_steps"].append(self.newton_its)
         self.history["alpha"].append(self.alpha_value)
         self.history["primal_increment"].append(increment)
         self.history["reason"].append(reason)
+        self.history["krylov_iterations"].append(self.krylov_outer)
         self.k += 1
         if increment < self.tol_exit or self.k >= self.max_outer:
             self.finished = True
+            self.solves_completed += 1
             return False
         if self.ctl is not None:
             self.ctl.accepted(self.newton_its)

@@ -455,6 +455,15 @@ class SNESProblem:
         dev.assemble_jacobian(x)
 
 
+class NotConvergedError(RuntimeError):
+    """Raised for ``snes_error_if_not_converged`` / ``ksp_error_if_not_converged`` (PETSc raises there); a device,
+    argument or communication failure is a ``_capi.LvppError`` instead and must not be mistaken for it."""
+
+    def __init__(self, message, reason, iterations):
+        super().__init__(message)
+        self.reason, self.iterations = reason, iterations
+
+
 class SNESSolver:
     """src/lvpp/problem.py:80-127."""
 
@@ -478,6 +487,7 @@ class SNESSolver:
 
     def solve(self):
         dev = self.problem.device_problem
+        self.converged_reason, self.iterations, self.linear_iterations = 0, 0, 0  # never report a previous solve
         dev.sync_coefficients()
         xh = self.problem.u.x.array
         if self._opts.snes_linesearch in (_capi.LINESEARCH_BT, _capi.LINESEARCH_L2):
@@ -566,7 +576,7 @@ class NonlinearProblem:
     def solve(self):
         reason, its = self._snes.solve()
         if reason == SNES_DIVERGED_LINEAR_SOLVE and _flag(self._options, "ksp_error_if_not_converged"):
-            raise RuntimeError("KSP did not converge (ksp_error_if_not_converged)")
+            raise NotConvergedError("KSP did not converge (ksp_error_if_not_converged)", reason, its)
         if reason <= 0 and _flag(self._options, "snes_error_if_not_converged"):
-            raise RuntimeError(f"SNES did not converge: reason {reason} after {its} iterations")
+            raise NotConvergedError(f"SNES did not converge: reason {reason} after {its} iterations", reason, its)
         return self.u

@@ -76,7 +76,7 @@ class _NumpyProblem:
         if reason > 0:  # u is overwritten only on convergence (src/lvpp/problem.py:121-123)
             self.sol.x.array[:] = xn
         elif self.raises:
-            raise RuntimeError("SNES did not converge")
+            raise obstacle_pg.NotConvergedError("SNES did not converge", reason, n)
 
 
 def _patched(monkeypatch, orc, max_it, fail_on=(), raises=False):

@@ -17,6 +17,8 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, default=215)
+    ap.add_argument("--nz", type=int, default=None, help="cubes along z over all ranks (default: --size)")
+    ap.add_argument("--tag", default="")
     ap.add_argument("--pc", default="mg")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--snes-rtol", dest="snes_rtol", type=float, default=None,
@@ -39,7 +41,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
     n = args.size
-    nz = world * max(2, round(n / world))
+    nz = args.nz if args.nz else world * max(2, round(n / world))
     t0 = time.perf_counter()
     msh = lvpp.mesh.create_box(n, n, nz, rank=rank, nranks=world)
     opts = {"ksp_rtol": 1e-12, "ksp_type": "gmres", "pc_type": "mg"} if args.pc == "mg" else {"ksp_rtol": 1e-12}
@@ -73,14 +75,19 @@ def main():
             return out
 
         st.dev.newton_step = logged
-    while st.step():
-        pass
+    failure = None
+    try:
+        while st.step():
+            pass
+    except lvpp.NotConvergedError as e:
+        failure = {"outer": st.k, "alpha": st.alpha_value, "newton": st.newton_its, "reason": e.reason}
     torch.cuda.synchronize()
     t_solve = time.perf_counter() - t1
     s = st.dev.stats()
     if rank == 0:
         print(json.dumps({
             "workload": f"3-D P1 obstacle LVPP, {n}x{n}x{nz} cubes x 6 tets, full solve ({args.alpha_scheme} alpha, alpha_max 1e2, tol 1e-4)",
+            "tag": args.tag, "linesearch": args.linesearch, "snes_rtol": args.snes_rtol, "failure": failure,
             "n_gpus": world, "rows": s["num_rows"], "setup_s": t_setup, "solve_s": t_solve,
             "newton_steps": st.total_newton, "krylov_iterations": st.total_krylov, "outer_steps": len(st.history["newton_steps"]),
             "dofs_per_sec": s["num_rows"] * st.total_newton / t_solve, "history": st.history,
