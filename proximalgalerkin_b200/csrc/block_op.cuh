@@ -124,6 +124,7 @@ struct PackedOpArgs {
   const double2* b;
   const double* binv;    // [Vown * 4]
   double omega;
+  const int* skip;       // device flag, non-zero = the Krylov solve is over, do nothing (null: always run)
 };
 
 // loads as volatile asm: the compiler otherwise sinks the next group's record loads below the current group's
@@ -141,6 +142,7 @@ __device__ __forceinline__ double2 lvpp_ld_pair(const double2* ptr) {
 
 template <int U, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_packed_op(PackedOpArgs p) {
+  if (p.skip && *p.skip) return;
   for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x; i0 < p.Vown; i0 += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = i0 + threadIdx.x;
     if (i >= p.Vown) continue;
@@ -215,6 +217,7 @@ struct Packed2OpArgs {
   const double2* b;
   const float4* binv;    // [Vown] single-precision node-block inverses
   double omega;
+  const int* skip;
 };
 
 __device__ __forceinline__ uint32_t lvpp_ld_u32(const uint32_t* ptr) {
@@ -227,6 +230,7 @@ __device__ __forceinline__ double lvpp_bf16_lo(uint32_t w) { return (double)__ui
 
 template <int UP, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_packed2_op(Packed2OpArgs p) {
+  if (p.skip && *p.skip) return;
   for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x; i0 < p.Vown; i0 += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = i0 + threadIdx.x;
     if (i >= p.Vown) continue;

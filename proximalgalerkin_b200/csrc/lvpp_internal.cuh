@@ -179,6 +179,7 @@ struct lvpp_problem {
   int64_t spmv_samples = 0;
   // one fine-level smoother sweep (k_packed_op, EPI_JACOBI) per V-cycle is bracketed by events (bench.py roofline)
   cudaEvent_t evp0 = nullptr, evp1 = nullptr;
+  cudaEvent_t evp0_cur = nullptr, evp1_cur = nullptr;  // the pair of the iteration being queued (evp*_ring)
   bool smooth_sample_pending = false, smooth_sample_recorded = false;
   double smooth_sampled_ms = 0.0;
   int64_t smooth_samples = 0, packed_op_launches = 0;
@@ -219,9 +220,16 @@ struct lvpp_problem {
   int gm_restart = 0;
   // classical Gram-Schmidt is repeated when less than eta2 of ||w||^2 survives the projection (Daniel et al.)
   double gm_eta2 = 0.01;         // (0.5 = Daniel's criterion; PETSc's default never repeats; profiles/r01_mg_scan.txt)
-  bool gm_weight_auto = false;    // experimental: equilibrated residual norm (weight on the psi rows), multigrid.cu
+  bool gm_weight_auto = true;     // equilibrated residual norm (weight on the psi rows), multigrid.cu; LVPP_GMRES_WEIGHT=off: Euclidean
   double gm_weight = 1.0, gm_weight_alpha = -1.0;
-  bool gm_fused_norm = false;     // experimental: ||w||^2 taken in the dot pass (one reduction per iteration)
+  // device-resident GMRES control (gmres_kernels.cuh: GmState): Hessenberg, rotations, residual estimate, decision
+  struct GmState* gm_state = nullptr;       // device
+  struct GmState* gm_state_host = nullptr;  // pinned [GM_RING + 2]: lagged per-iteration copies, cycle-end copy, upload staging
+  double *gm_H = nullptr, *gm_cs = nullptr, *gm_sn = nullptr, *gm_g = nullptr, *gm_yv = nullptr;  // device
+  double* gm_red = nullptr;       // device [8] reduced norms
+  cudaEvent_t gm_ev[8] = {nullptr};                  // status copy of iteration j landed (ring)
+  cudaEvent_t evs0_ring[8] = {nullptr}, evs1_ring[8] = {nullptr}, evp0_ring[8] = {nullptr}, evp1_ring[8] = {nullptr};
+  const int* gm_skip = nullptr;   // non-null inside a GMRES iteration: the large kernels of the cycle return at once when set
   double* gm_h = nullptr;         // device [restart + 2]
   double* gm_h_host = nullptr;    // pinned
   double* gm_part = nullptr;      // partial sums [(restart + 2) * npartials]

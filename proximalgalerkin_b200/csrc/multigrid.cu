@@ -676,8 +676,7 @@ int lvpp_mg_setup(lvpp_problem* h) {
   h->mg_margin = env_double("LVPP_MG_MARGIN", h->mg_margin);
   h->mg_power_its = (int)env_double("LVPP_MG_POWER_ITS", h->mg_power_its);
   h->gm_eta2 = env_double("LVPP_GMRES_ETA2", h->gm_eta2);
-  h->gm_fused_norm = env_double("LVPP_GMRES_FUSED_NORM", 0.0) != 0.0;
-  if (const char* gw = getenv("LVPP_GMRES_WEIGHT")) h->gm_weight_auto = strcmp(gw, "auto") == 0;
+  if (const char* gw = getenv("LVPP_GMRES_WEIGHT")) h->gm_weight_auto = strcmp(gw, "off") != 0;
   // GMRES workspace (also the scratch of the collective decisions below)
   h->gm_restart = (int)env_double("LVPP_GMRES_RESTART", 50);
   if (h->gm_restart < 2 || h->gm_restart > 200) { lvpp_set_error("bad LVPP_GMRES_RESTART"); return LVPP_E_INVALID; }
@@ -688,6 +687,24 @@ int lvpp_mg_setup(lvpp_problem* h) {
   h->gm_flexible = env_double("LVPP_GMRES_FLEXIBLE", 0.0) != 0.0;
   if (h->gm_flexible) CKR(lvpp_dalloc(h, &h->gm_Z, (size_t)h->gm_restart * 2 * h->V));
   CKR(lvpp_dalloc(h, &h->gm_h, (size_t)h->gm_restart + 72));
+  {
+    const size_t m = (size_t)h->gm_restart;
+    CKR(lvpp_dalloc(h, &h->gm_state, 1));
+    CKR(lvpp_dalloc(h, &h->gm_H, (m + 1) * m));
+    CKR(lvpp_dalloc(h, &h->gm_cs, m));
+    CKR(lvpp_dalloc(h, &h->gm_sn, m));
+    CKR(lvpp_dalloc(h, &h->gm_g, m + 1));
+    CKR(lvpp_dalloc(h, &h->gm_yv, m));
+    CKR(lvpp_dalloc(h, &h->gm_red, 8));
+    CK(cudaMallocHost((void**)&h->gm_state_host, sizeof(GmState) * (GM_RING + 2)));
+    for (int i = 0; i < GM_RING; ++i) {
+      CK(cudaEventCreateWithFlags(&h->gm_ev[i], cudaEventDisableTiming));
+      CK(cudaEventCreate(&h->evs0_ring[i]));
+      CK(cudaEventCreate(&h->evs1_ring[i]));
+      CK(cudaEventCreate(&h->evp0_ring[i]));
+      CK(cudaEventCreate(&h->evp1_ring[i]));
+    }
+  }
   CKR(lvpp_dalloc(h, &h->gm_part, (size_t)(h->gm_restart + 2) * h->npartials));
   CK(cudaMallocHost((void**)&h->gm_h_host, sizeof(double) * (h->gm_restart + 72)));
   h->levels.clear();
@@ -785,13 +802,14 @@ static int level_op_local(lvpp_problem* h, MgLevel& L, int epi, double omega, co
     Packed2OpArgs q;
     q.Vown = L.Vown; q.slice_ptr = L.slice_ptr; q.P2 = L.P2; q.Pd = L.Pd; q.bc_flag = L.bc_flag;
     q.v = (const double2*)v; q.y = (double2*)y; q.epi = epi; q.b = (const double2*)b; q.binv = L.binv32; q.omega = omega;
+    q.skip = h->gm_skip;
     const bool sample = &L == &h->levels[0] && epi == EPI_JACOBI && h->smooth_sample_pending;
-    if (sample) CK(cudaEventRecord(h->evp0, h->stream));
+    if (sample) CK(cudaEventRecord(h->evp0_cur, h->stream));
     if (h->mg_unroll == 8) LAUNCH(h, (k_packed2_op<4, 3>), lvpp_grid(L.Vown, 256, 3), 256, 0, q);
     else LAUNCH(h, (k_packed2_op<2, 4>), lvpp_grid(L.Vown, 256, 4), 256, 0, q);
     if (&L == &h->levels[0]) h->packed_op_launches++;
     if (sample) {
-      CK(cudaEventRecord(h->evp1, h->stream));
+      CK(cudaEventRecord(h->evp1_cur, h->stream));
       h->smooth_sample_pending = false;
       h->smooth_sample_recorded = true;
     }
@@ -799,13 +817,14 @@ static int level_op_local(lvpp_problem* h, MgLevel& L, int epi, double omega, co
     PackedOpArgs q;
     q.Vown = L.Vown; q.slice_ptr = L.slice_ptr; q.P = L.P; q.bc_flag = L.bc_flag;
     q.v = (const double2*)v; q.y = (double2*)y; q.epi = epi; q.b = (const double2*)b; q.binv = L.binv; q.omega = omega;
+    q.skip = h->gm_skip;
     const bool sample = &L == &h->levels[0] && epi == EPI_JACOBI && h->smooth_sample_pending;
-    if (sample) CK(cudaEventRecord(h->evp0, h->stream));
+    if (sample) CK(cudaEventRecord(h->evp0_cur, h->stream));
     if (h->mg_unroll == 8) LAUNCH(h, (k_packed_op<8, 3>), lvpp_grid(L.Vown, 256, 3), 256, 0, q);
     else LAUNCH(h, (k_packed_op<4, 4>), lvpp_grid(L.Vown, 256, 4), 256, 0, q);
     if (&L == &h->levels[0]) h->packed_op_launches++;
     if (sample) {
-      CK(cudaEventRecord(h->evp1, h->stream));
+      CK(cudaEventRecord(h->evp1_cur, h->stream));
       h->smooth_sample_pending = false;
       h->smooth_sample_recorded = true;
     }
@@ -817,6 +836,7 @@ static int level_op_local(lvpp_problem* h, MgLevel& L, int epi, double omega, co
     p.b = (const double2*)b;
     p.binv = L.binv;
     p.omega = omega;
+    p.skip_flag = h->gm_skip;
     LAUNCH(h, (k_block_op<0>), grid, 256, 0, p);
   }
   CK(cudaGetLastError());
@@ -1069,6 +1089,11 @@ static int reduce_to_host(lvpp_problem* h, double* partials, int nvals, double* 
 
 int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_newton_opts* o, int32_t* its_out,
                   int32_t* reason_out, double* rnorm_out) {
+  // Restarted GMRES with the whole recurrence on the device (gmres_kernels.cuh: GmState, k_gm_*): an iteration is a
+  // fixed list of launches -- cycle, J*v, two guarded Gram-Schmidt passes, the Givens update of the Hessenberg column,
+  // the scaling of the new basis vector -- with NO host round trip.  The host reads a copy of the state one iteration
+  // late (it waits for the copy of iteration j - 1 only after iteration j is queued, so the stream never drains) and
+  // stops queueing once `conv` is set; whatever was queued behind the deciding iteration returns at once.
   const int m = h->gm_restart;
   const int64_t Vown = h->Vown, stride2 = h->V;  // basis vectors are 2V doubles = V double2
   const int nb = h->npartials;
@@ -1076,18 +1101,15 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
   double* gpart = h->gm_part;  // partial sums [(m + 2) * nb]
   const int maxit = o->ksp_max_it > 0 ? o->ksp_max_it : 1000;
   CK(cudaEventRecord(h->ev0, h->stream));
-  std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), yv(m);
   auto vec = [&](int k) { return (double*)(Vb + (int64_t)k * stride2); };
-  int total = 0, reason = 0;
-  double bnorm = 0.0, rnorm = 0.0, tol = 0.0;
-  bool first = true;
   MgLevel& L0 = h->levels[0];
-  // Equilibrated residual norm (LVPP_GMRES_WEIGHT=auto, experimental, off by default): the rows of the u equation
+  // Equilibrated residual norm (the default; LVPP_GMRES_WEIGHT=off for the Euclidean one): the rows of the u equation
   // carry entries of size alpha K_ii, those of the psi equation entries of size M_ii = O(h^2 / alpha) times that, and a
-  // Euclidean residual norm all but ignores the latter.  On the developed contact set this is what makes restarted
-  // GMRES stagnate (tools/full_solve_cpu.py: 72 - 300+ iterations on a 40^3 mesh at alpha = 5.3 against 28 with the
-  // weight; 600+ at 64^3).  With the weight wy = sum alpha K_ii / sum M_ii on the psi component of every inner product
-  // GMRES runs on S J S, S = diag(1, sqrt(wy)), without touching the operator or the cycle.
+  // Euclidean residual norm all but ignores the latter.  With the weight wy = sum alpha K_ii / sum M_ii on the psi
+  // component of every inner product GMRES runs on S J S, S = diag(1, sqrt(wy)), without touching the operator or the
+  // cycle.  Measured at n = 215 (profiles/r02_diag215_*.txt): 22 - 29 Krylov iterations per Newton step through the
+  // first two proximal steps against 27 - 57, identical Newton iterates (both norms leave residuals of 1e-15 of the
+  // right-hand side in BOTH row blocks at ksp_rtol 1e-12).
   double wy = 1.0;
   if (h->gm_weight_auto) {
     if (!(h->gm_weight_alpha == h->alpha)) {
@@ -1100,141 +1122,127 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
     }
     wy = h->gm_weight;
   }
+  GmState* st = h->gm_state;
+  GmState* ring = h->gm_state_host;            // [0, GM_RING): lagged copies; [GM_RING]: cycle-end copy; [GM_RING + 1]: upload
+  {
+    GmState init;
+    memset(&init, 0, sizeof(init));
+    init.rtol = o->ksp_rtol; init.atol = o->ksp_atol; init.eta2 = h->gm_eta2; init.maxit = maxit; init.first = 1;
+    ring[GM_RING + 1] = init;
+    CK(cudaMemcpyAsync(st, &ring[GM_RING + 1], sizeof(GmState), cudaMemcpyHostToDevice, h->stream));
+  }
+  const int* skip = &st->conv;
   CK(cudaMemsetAsync(d_y, 0, sizeof(double) * 2 * h->V, h->stream));
-  while (reason == 0) {
+  bool smooth_rec[GM_RING] = {false};
+  auto take_samples = [&](int slot) -> int {  // the event pairs of a finished iteration
+    float sms = 0.f;
+    CK(cudaEventElapsedTime(&sms, h->evs0_ring[slot], h->evs1_ring[slot]));
+    h->spmv_sampled_ms += sms;
+    h->spmv_samples++;
+    if (smooth_rec[slot]) {
+      CK(cudaEventElapsedTime(&sms, h->evp0_ring[slot], h->evp1_ring[slot]));
+      h->smooth_sampled_ms += sms;
+      h->smooth_samples++;
+    }
+    return 0;
+  };
+  int reason = 0;
+  bool first = true;
+  GmState fin;
+  memset(&fin, 0, sizeof(fin));
+  while (true) {
     // r = rhs - J y  (first cycle: y = 0)
     if (first) {
       CK(cudaMemcpyAsync(vec(0), d_rhs, sizeof(double) * 2 * Vown, cudaMemcpyDeviceToDevice, h->stream));
+      first = false;
     } else {
       CKR(level_op(h, L0, EPI_RESID, 1.0, d_y, d_rhs, vec(0), false));
     }
     LAUNCH(h, k_multi_dot, nb, 256, 0, Vown, Vb, stride2, 0, 1, (const double2*)vec(0), nb, gpart, wy);
+    LAUNCH(h, k_reduce_multi, 1, 256, 0, nb, 1, gpart, h->gm_red);
     CK(cudaGetLastError());
-    CKR(reduce_to_host(h, gpart, 1, h->gm_h, h->gm_h_host));
-    rnorm = sqrt(h->gm_h_host[0]);
-    if (first) {
-      bnorm = rnorm;
-      tol = std::max(o->ksp_rtol * bnorm, o->ksp_atol);
-      first = false;
-    }
-    if (!std::isfinite(rnorm)) { reason = LVPP_KSP_DIVERGED_NANORINF; break; }
-    if (rnorm <= tol) { reason = rnorm <= o->ksp_atol ? LVPP_KSP_CONVERGED_ATOL : LVPP_KSP_CONVERGED_RTOL; break; }
-    LAUNCH(h, k_axpby, nb, 256, 0, Vown, 1.0 / rnorm, (const double2*)vec(0), 0, (double2*)vec(0));
+    if (h->nranks > 1) CKR(lvpp_allreduce_sum(h, h->gm_red, 1));
+    LAUNCH(h, k_gm_cycle_begin, 1, 1, 0, st, h->gm_red, h->gm_g, m);
+    LAUNCH(h, k_gm_scale, nb, 256, 0, Vown, st, (double2*)vec(0));
     CK(cudaGetLastError());
-    std::fill(g.begin(), g.end(), 0.0);
-    g[0] = rnorm;
-    int j = 0;
-    for (; j < m; ++j) {
+    int j = 0, polled = 0;  // iterations queued / iterations whose state copy the host has looked at
+    bool over = false;
+    for (; j < m && !over; ++j) {
+      const int slot = j % GM_RING;
       // w = J M^-1 v_j  -> stored in v_{j+1}
       double* z = nullptr;
+      h->gm_skip = skip;
+      h->evp0_cur = h->evp0_ring[slot];
+      h->evp1_cur = h->evp1_ring[slot];
       h->smooth_sample_pending = true;
       h->smooth_sample_recorded = false;
-      CKR(lvpp_mg_vcycle(h, vec(j), &z));
+      int rc = lvpp_mg_vcycle(h, vec(j), &z);
       h->smooth_sample_pending = false;
+      smooth_rec[slot] = h->smooth_sample_recorded;
+      if (rc) { h->gm_skip = nullptr; return rc; }
       if (h->gm_Z)  // FGMRES: keep Z_j (owned entries; y's ghosts are refreshed by the next residual)
         CK(cudaMemcpyAsync(h->gm_Z + (size_t)j * 2 * stride2, z, sizeof(double) * 2 * Vown, cudaMemcpyDeviceToDevice, h->stream));
-      if (h->nranks > 1) CKR(lvpp_halo_forward_level(h, h->halo, z));
-      CK(cudaEventRecord(h->evs0, h->stream));
-      CKR(level_op_local(h, L0, EPI_NONE, 1.0, z, nullptr, vec(j + 1)));
-      CK(cudaEventRecord(h->evs1, h->stream));
-      double* hcol = &H[(size_t)j * (m + 1)];
-      for (int k = 0; k <= j + 1; ++k) hcol[k] = 0.0;
-      double beta = 0.0;
+      if (h->nranks > 1) { rc = lvpp_halo_forward_level(h, h->halo, z); if (rc) { h->gm_skip = nullptr; return rc; } }
+      CK(cudaEventRecord(h->evs0_ring[slot], h->stream));
+      rc = level_op_local(h, L0, EPI_NONE, 1.0, z, nullptr, vec(j + 1));
+      h->gm_skip = nullptr;
+      if (rc) return rc;
+      CK(cudaEventRecord(h->evs1_ring[slot], h->stream));
+      double* Hcol = h->gm_H + (size_t)j * (m + 1);
       for (int pass = 0; pass < 2; ++pass) {
-        // LVPP_GMRES_FUSED_NORM=1 (experimental, off by default): the first pass also takes w . w (w is basis slot
-        // j + 1), so that beta^2 = ||w||^2 - sum h_k^2 needs no second reduction / host synchronisation; the explicit
-        // norm is only fetched when the re-orthogonalisation test fails (then beta^2 is a small difference)
-        const bool fused = h->gm_fused_norm && pass == 0;
-        const int ndots = fused ? j + 2 : j + 1;
-        for (int k0 = 0; k0 < ndots; k0 += GM_CHUNK) {
-          const int nv = std::min(GM_CHUNK, ndots - k0);
-          LAUNCH(h, k_multi_dot, nb, 256, 0, Vown, Vb, stride2, k0, nv, (const double2*)vec(j + 1), nb, gpart, wy);
+        // classical Gram-Schmidt; pass 1 (selective re-orthogonalisation) returns at once unless pass 0 asked for it
+        for (int k0 = 0; k0 <= j; k0 += GM_CHUNK) {
+          const int nv = std::min(GM_CHUNK, j + 1 - k0);
+          LAUNCH(h, k_multi_dot, nb, 256, 0, Vown, Vb, stride2, k0, nv, (const double2*)vec(j + 1), nb, gpart, wy, st, pass);
         }
+        LAUNCH(h, k_reduce_multi, (j + 1) < 64 ? (j + 1) : 64, 256, 0, nb, j + 1, gpart, h->gm_h, st, pass);
         CK(cudaGetLastError());
-        CKR(reduce_to_host(h, gpart, ndots, h->gm_h, h->gm_h_host));
-        double hsq = 0.0;
-        for (int k = 0; k <= j; ++k) { hcol[k] += h->gm_h_host[k]; hsq += h->gm_h_host[k] * h->gm_h_host[k]; }
-        const double ww = fused ? h->gm_h_host[j + 1] : 0.0;
-        // coefficients are already on the device in gm_h (all-reduced)
-        LAUNCH(h, k_gmres_update, nb, 256, 0, Vown, Vb, stride2, j + 1, h->gm_h, (double2*)vec(j + 1), nb, m + 1, gpart, wy);
+        if (h->nranks > 1) CKR(lvpp_allreduce_sum(h, h->gm_h, j + 1));
+        LAUNCH(h, k_gmres_update, nb, 256, 0, Vown, Vb, stride2, j + 1, h->gm_h, (double2*)vec(j + 1), nb, m + 1, gpart, wy, st, pass);
+        LAUNCH(h, k_reduce_multi, 1, 256, 0, nb, 1, gpart + (size_t)(m + 1) * nb, h->gm_red + 1, st, pass);
         CK(cudaGetLastError());
-        bool have_beta = false;
-        if (fused && ww - hsq > h->gm_eta2 * ww) {
-          beta = sqrt(ww - hsq);
-          have_beta = true;
-        }
-        if (!have_beta) {
-          CKR(reduce_to_host(h, gpart + (size_t)(m + 1) * nb, 1, h->gm_h + m + 2, h->gm_h_host + m + 2));
-          beta = sqrt(h->gm_h_host[m + 2]);
-        }
-        if (pass == 0) {
-          float sms = 0.f;
-          CK(cudaEventElapsedTime(&sms, h->evs0, h->evs1));
-          h->spmv_sampled_ms += sms;
-          h->spmv_samples++;
-          if (h->smooth_sample_recorded) {
-            CK(cudaEventElapsedTime(&sms, h->evp0, h->evp1));
-            h->smooth_sampled_ms += sms;
-            h->smooth_samples++;
-            h->smooth_sample_recorded = false;
-          }
-        }
-        // selective re-orthogonalisation (Daniel et al.): only when the projection removed most of w
-        if (beta * beta > h->gm_eta2 * (hsq + beta * beta)) break;
+        if (h->nranks > 1) CKR(lvpp_allreduce_sum(h, h->gm_red + 1, 1));
+        LAUNCH(h, k_gm_after_pass, 1, 1, 0, st, j, pass, h->gm_h, h->gm_red + 1, Hcol, h->gm_cs, h->gm_sn, h->gm_g);
+        CK(cudaGetLastError());
       }
-      hcol[j + 1] = beta;
-      ++total;
-      // Givens
-      for (int k = 0; k < j; ++k) {
-        const double t = cs[k] * hcol[k] + sn[k] * hcol[k + 1];
-        hcol[k + 1] = -sn[k] * hcol[k] + cs[k] * hcol[k + 1];
-        hcol[k] = t;
+      LAUNCH(h, k_gm_scale, nb, 256, 0, Vown, st, (double2*)vec(j + 1));
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(&ring[slot], st, sizeof(GmState), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaEventRecord(h->gm_ev[slot], h->stream));
+      if (j >= 1) {  // look at iteration j - 1 while iteration j keeps the device busy
+        const int ps = (j - 1) % GM_RING;
+        CK(cudaEventSynchronize(h->gm_ev[ps]));
+        over = ring[ps].conv != 0;
+        if (ring[ps].ncols == j) CKR(take_samples(ps));  // (not a skipped iteration)
+        polled = j;
       }
-      const double den = std::hypot(hcol[j], hcol[j + 1]);
-      cs[j] = den > 0 ? hcol[j] / den : 1.0;
-      sn[j] = den > 0 ? hcol[j + 1] / den : 0.0;
-      hcol[j] = den;
-      hcol[j + 1] = 0.0;
-      g[j + 1] = -sn[j] * g[j];
-      g[j] = cs[j] * g[j];
-      rnorm = fabs(g[j + 1]);
-      if (!std::isfinite(rnorm)) { reason = LVPP_KSP_DIVERGED_NANORINF; ++j; break; }
-      const bool conv = rnorm <= tol;
-      if (conv || beta == 0.0 || total >= maxit) {
-        ++j;
-        if (conv) reason = rnorm <= o->ksp_atol ? LVPP_KSP_CONVERGED_ATOL : LVPP_KSP_CONVERGED_RTOL;
-        else if (beta == 0.0) reason = LVPP_KSP_CONVERGED_RTOL;  // happy breakdown: exact solution in the space
-        else reason = LVPP_KSP_DIVERGED_ITS;
-        break;
+    }
+    // end of the restart cycle (or of the solve): the state after everything queued so far
+    CK(cudaMemcpyAsync(&ring[GM_RING], st, sizeof(GmState), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    fin = ring[GM_RING];
+    for (int q = polled; q < j; ++q)
+      if (q < fin.ncols) CKR(take_samples(q % GM_RING));
+    const int k = fin.ncols;  // columns used
+    if (fin.conv && fin.reason == LVPP_KSP_DIVERGED_NANORINF) { reason = fin.reason; break; }
+    if (k > 0) {
+      // back substitution on the device, y += M^-1 (V yv); the combination goes to v_k (v_0..v_{k-1} are the basis)
+      LAUNCH(h, k_gm_backsolve, 1, 1, 0, k, m, h->gm_H, h->gm_g, h->gm_yv);
+      double* comb = vec(k);
+      if (h->gm_Z) {  // FGMRES: y += Z yv
+        LAUNCH(h, k_lincomb, nb, 256, 0, Vown, (const double2*)h->gm_Z, stride2, k, h->gm_yv, (double2*)comb);
+        CK(cudaGetLastError());
+        LAUNCH(h, k_axpby, nb, 256, 0, Vown, 1.0, (const double2*)comb, 1, (double2*)d_y);
+      } else {
+        LAUNCH(h, k_lincomb, nb, 256, 0, Vown, Vb, stride2, k, h->gm_yv, (double2*)comb);
+        CK(cudaGetLastError());
+        double* z = nullptr;
+        CKR(lvpp_mg_vcycle(h, comb, &z));
+        LAUNCH(h, k_axpby, nb, 256, 0, Vown, 1.0, (const double2*)z, 1, (double2*)d_y);
       }
-      LAUNCH(h, k_axpby, nb, 256, 0, Vown, 1.0 / beta, (const double2*)vec(j + 1), 0, (double2*)vec(j + 1));
       CK(cudaGetLastError());
     }
-    const int k = j;  // columns used
-    if (reason == LVPP_KSP_DIVERGED_NANORINF) break;
-    // back substitution, y += M^-1 (V yv)
-    for (int i = k - 1; i >= 0; --i) {
-      double s = g[i];
-      for (int c = i + 1; c < k; ++c) s -= H[(size_t)c * (m + 1) + i] * yv[c];
-      yv[i] = s / H[(size_t)i * (m + 1) + i];
-    }
-    for (int i = 0; i < k; ++i) h->gm_h_host[i] = yv[i];
-    CK(cudaMemcpyAsync(h->gm_h, h->gm_h_host, sizeof(double) * k, cudaMemcpyHostToDevice, h->stream));
-    // the combination goes to v_m (free: k <= m columns use v_0..v_{k-1}; v_k holds w and is dead)
-    double* comb = vec(k);
-    if (h->gm_Z) {  // FGMRES: y += Z yv
-      LAUNCH(h, k_lincomb, nb, 256, 0, Vown, (const double2*)h->gm_Z, stride2, k, h->gm_h, (double2*)comb);
-      CK(cudaGetLastError());
-      LAUNCH(h, k_axpby, nb, 256, 0, Vown, 1.0, (const double2*)comb, 1, (double2*)d_y);
-    } else {
-      LAUNCH(h, k_lincomb, nb, 256, 0, Vown, Vb, stride2, k, h->gm_h, (double2*)comb);
-      CK(cudaGetLastError());
-      double* z = nullptr;
-      CKR(lvpp_mg_vcycle(h, comb, &z));
-      LAUNCH(h, k_axpby, nb, 256, 0, Vown, 1.0, (const double2*)z, 1, (double2*)d_y);
-    }
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(h->stream));  // gm_h_host is reused by the next cycle
+    if (fin.conv) { reason = fin.reason; break; }
   }
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaEventSynchronize(h->ev1));
@@ -1242,9 +1250,9 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->t_krylov_ms += ms;
-  h->krylov_its += total;
-  if (its_out) *its_out = total;
+  h->krylov_its += fin.total;
+  if (its_out) *its_out = fin.total;
   if (reason_out) *reason_out = reason;
-  if (rnorm_out) *rnorm_out = rnorm;
+  if (rnorm_out) *rnorm_out = fin.rnorm;
   return 0;
 }

@@ -515,6 +515,14 @@ extern "C" int lvpp_destroy(lvpp_handle h) {
   if (h->evs1) cudaEventDestroy(h->evs1);
   if (h->evp0) cudaEventDestroy(h->evp0);
   if (h->evp1) cudaEventDestroy(h->evp1);
+  for (int i = 0; i < 8; ++i) {
+    if (h->gm_ev[i]) cudaEventDestroy(h->gm_ev[i]);
+    if (h->evs0_ring[i]) cudaEventDestroy(h->evs0_ring[i]);
+    if (h->evs1_ring[i]) cudaEventDestroy(h->evs1_ring[i]);
+    if (h->evp0_ring[i]) cudaEventDestroy(h->evp0_ring[i]);
+    if (h->evp1_ring[i]) cudaEventDestroy(h->evp1_ring[i]);
+  }
+  if (h->gm_state_host) cudaFreeHost(h->gm_state_host);
   if (h->evt0) cudaEventDestroy(h->evt0);
   if (h->evt1) cudaEventDestroy(h->evt1);
   if (h->stream) cudaStreamDestroy(h->stream);
