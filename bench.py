@@ -205,7 +205,7 @@ def run_b200(args):
     msh = lvpp.mesh.create_box(nxy, nxy, nz, lo=lo, hi=hi, rank=rank, nranks=world)
     opts = {"ksp_rtol": args.ksp_rtol, "ksp_max_it": 200000}
     if args.pc == "mg":
-        opts = {"ksp_rtol": args.ksp_rtol, "ksp_type": "gmres", "pc_type": "mg"}
+        opts = {"ksp_rtol": args.ksp_rtol, "ksp_type": "gmres", "pc_type": "mg", "ksp_max_it": 400}
     st = lvpp.obstacle_pg.LvppStepper(msh, 1, "double_exponential", 1e2, 1e-4, petsc_options=opts,
                                       obstacle_period=2.0 if slabs > 1 else None, obstacle_origin=-float(slabs))
     dev = st.dev

@@ -231,22 +231,6 @@ int lvpp_solve_linear(lvpp_problem* h, const double* d_rhs, double* d_y, const l
     CKR(lvpp_mg_update(h));
     int32_t its1 = 0, reason1 = 0;
     CKR(lvpp_gmres_mg(h, d_rhs, d_y, o, &its1, &reason1, rnorm));
-    if (reason1 < 0) {
-      // the Chebyshev sweeps amplify eigenvalues above their interval: a diverged / stagnated solve is retried once
-      // with eigenvalue estimates redone from scratch
-      int32_t its2 = 0;
-      // ... and in the equilibrated residual norm (multigrid.cu:lvpp_gmres_mg), from here on: every stagnating solve of
-      // the CPU emulation of whole LVPP solves converges in 17 - 40 iterations with it.  The default
-      // path is untouched: this only runs after a solve has already failed.  LVPP_GMRES_WEIGHT=off forbids it.
-      const char* gw = getenv("LVPP_GMRES_WEIGHT");
-      if (!(gw && strcmp(gw, "off") == 0) && !h->gm_weight_auto) {
-        h->gm_weight_auto = true;
-        if (getenv("LVPP_MG_VERBOSE") && h->rank == 0) fprintf(stderr, "[lvpp mg] Krylov solve failed: equilibrated residual norm from here on\n");
-      }
-      CKR(lvpp_mg_reestimate(h));
-      CKR(lvpp_gmres_mg(h, d_rhs, d_y, o, &its2, &reason1, rnorm));
-      its1 += its2;
-    }
     // The Chebyshev dampings pay in the first proximal step (26 - 30 Krylov iterations per Newton step at n = 215
     // against 32 - 35 with plain damping) and lose later: once the contact set has developed (exp(psi) -> 0 on it)
     // the solves of the second proximal step take 49 - 60 iterations with ratio 10 against 38 - 39 with plain damping,
