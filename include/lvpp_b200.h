@@ -171,6 +171,8 @@ int lvpp_get_csr_pattern(lvpp_handle h, int64_t* h_indptr, int32_t* h_indices);
 /* ---- state mutated by the outer proximal loop ---- */
 /* alpha.value = ... (obstacle_pg.py:176-183) */
 int lvpp_set_alpha(lvpp_handle h, double alpha);
+/* f.value = ... : the forcing Constant of obstacle_pg.py:74,122 (dolfinx reads constants at assembly time) */
+int lvpp_set_forcing(lvpp_handle h, double f);
 /* sol_k.x.array[:] = ... (obstacle_pg.py:158,226); d_xk [2*num_nodes] */
 int lvpp_set_previous(lvpp_handle h, const double* d_xk);
 
@@ -211,6 +213,9 @@ int lvpp_observables(lvpp_handle h, const double* d_x, double* h_out6);
 int lvpp_newton_solve_host(lvpp_handle h, double* h_x, const lvpp_newton_opts* opts, int32_t* its,
                            int32_t* reason, double* h_fnorm, int32_t* linear_its);
 int lvpp_set_previous_host(lvpp_handle h, const double* h_xk);
+/* the last Newton iterate of lvpp_newton_solve_host whatever its reason (dolfinx.fem.petsc.NonlinearProblem.solve leaves
+ * it in u, obstacle_pg.py:190; SNESSolver.solve of src/lvpp/problem.py:121-123 keeps u on failure); h_x [2 * num_nodes] */
+int lvpp_get_last_iterate_host(lvpp_handle h, double* h_x);
 
 /* ---- measurement helpers ---- */
 /* CUDA events on the handle's stream: start, then stop returns the elapsed device time in ms */

@@ -526,12 +526,20 @@ extern "C" int lvpp_set_alpha(lvpp_handle h, double alpha) {
   return LVPP_OK;
 }
 
+// f.value = ... (obstacle_pg.py:74: a dolfinx Constant is read at assembly time, so a driver may change it between solves)
+extern "C" int lvpp_set_forcing(lvpp_handle h, double f) {
+  if (!h) { lvpp_set_error("null handle"); return LVPP_E_INVALID; }
+  if (!std::isfinite(f)) { lvpp_set_error("forcing must be finite"); return LVPP_E_INVALID; }
+  h->f = f;
+  return LVPP_OK;
+}
+
 extern "C" int lvpp_set_previous(lvpp_handle h, const double* d_xk) {
   CHECK_H(h);
   if (!d_xk) { lvpp_set_error("null argument"); return LVPP_E_INVALID; }
   CK(cudaMemcpyAsync(h->xk, d_xk, sizeof(double) * 2 * h->V, cudaMemcpyDeviceToDevice, h->stream));
   if (h->nranks > 1) CKR(lvpp_halo_forward_impl(h, h->xk));
-  CK(cudaStreamSynchronize(h->stream));
+  CKR(lvpp_sync_check_comm(h));
   return LVPP_OK;
 }
 
@@ -540,7 +548,7 @@ extern "C" int lvpp_set_previous_host(lvpp_handle h, const double* h_xk) {
   if (!h_xk) { lvpp_set_error("null argument"); return LVPP_E_INVALID; }
   CK(cudaMemcpyAsync(h->xk, h_xk, sizeof(double) * 2 * h->V, cudaMemcpyHostToDevice, h->stream));
   if (h->nranks > 1) CKR(lvpp_halo_forward_impl(h, h->xk));
-  CK(cudaStreamSynchronize(h->stream));
+  CKR(lvpp_sync_check_comm(h));
   return LVPP_OK;
 }
 
@@ -549,7 +557,7 @@ extern "C" int lvpp_assemble_residual(lvpp_handle h, const double* d_x, double* 
   if (!d_x || !d_F) { lvpp_set_error("null argument"); return LVPP_E_INVALID; }
   CKR(lvpp_eval_residual(h, d_x, d_F, true));
   CK(cudaMemcpyAsync(h->red_host, h->scal->red, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  CKR(lvpp_sync_check_comm(h));
   if (h_fnorm) *h_fnorm = sqrt(h->red_host[0]);
   return LVPP_OK;
 }
@@ -559,7 +567,7 @@ extern "C" int lvpp_assemble_jacobian(lvpp_handle h, const double* d_x) {
   if (!d_x) { lvpp_set_error("null argument"); return LVPP_E_INVALID; }
   if (h->nranks > 1) CKR(lvpp_halo_forward_impl(h, const_cast<double*>(d_x)));
   CKR(assemble_D(h, d_x));
-  CK(cudaStreamSynchronize(h->stream));
+  CKR(lvpp_sync_check_comm(h));
   return LVPP_OK;
 }
 
@@ -580,7 +588,7 @@ extern "C" int lvpp_spmv(lvpp_handle h, const double* d_v, double* d_y) {
   if (!h->jac_valid) { lvpp_set_error("no Jacobian assembled yet"); return LVPP_E_INVALID; }
   if (h->nranks > 1) CKR(lvpp_halo_forward_impl(h, const_cast<double*>(d_v)));
   CKR(lvpp_apply_jacobian(h, d_v, d_y, nullptr, nullptr, nullptr));
-  CK(cudaStreamSynchronize(h->stream));
+  CKR(lvpp_sync_check_comm(h));
   return LVPP_OK;
 }
 
@@ -602,7 +610,7 @@ extern "C" int lvpp_observables(lvpp_handle h, const double* d_x, double* h_out6
   CK(cudaGetLastError());
   CKR(lvpp_reduce_partials(h, 6, h->scal->red));
   CK(cudaMemcpyAsync(h->red_host, h->scal->red, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  CKR(lvpp_sync_check_comm(h));
   for (int i = 0; i < 6; ++i) h_out6[i] = h->red_host[i];
   return LVPP_OK;
 }

@@ -152,7 +152,7 @@ struct HaloPush {
 __global__ void __launch_bounds__(256) k_halo_p2p(HaloPush hp, const int32_t* __restrict__ send_nodes,
                                                    const int32_t* __restrict__ recv_nodes, int64_t nrecv, double2* __restrict__ v,
                                                    const double2* __restrict__ rbuf, volatile unsigned long long* flags,
-                                                   int* __restrict__ counter, unsigned long long seq, int* __restrict__ err) {
+                                                   int* __restrict__ counter, unsigned long long seq, int* __restrict__ err, long long timeout) {
   const int64_t nsend = hp.send_ptr[hp.nb];
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nsend; p += (int64_t)gridDim.x * blockDim.x) {
     int b = 0;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) k_halo_p2p(HaloPush hp, const int32_t* __
     for (int b = 0; b < hp.nb; ++b) {
       const long long t0 = clock64();
       while (flags[b] < seq)
-        if (clock64() - t0 > (1LL << 34)) {  // ~8 s: a peer died or the call sequences diverged
+        if (clock64() - t0 > timeout) {  // a peer died or the call sequences diverged (default ~8 s)
           *err = 1;
           break;
         }
@@ -196,6 +196,10 @@ int lvpp_halo_p2p_setup(lvpp_problem* h, LevelHalo& H) {
   if (h->nranks <= 1) return 0;
   const char* mode = getenv("LVPP_HALO");
   const bool want = !(mode && strcmp(mode, "nccl") == 0);
+  if (const char* to = getenv("LVPP_HALO_TIMEOUT_S")) {  // how long k_halo_p2p waits for a neighbour's flag
+    const double sec = atof(to);
+    if (sec > 0.0) h->halo_timeout_ticks = (long long)(sec * 1.9e9);  // clock64 runs at the SM clock (<= 1.965 GHz)
+  }
   const int nb = H.num_neighbors;
   const int64_t nr = H.recv_ptr.back();
   const size_t flag_bytes = 256, buf_bytes = sizeof(double) * 2 * (size_t)(nr > 0 ? nr : 1);
@@ -285,7 +289,7 @@ static int halo_forward_p2p(lvpp_problem* h, LevelHalo& H, double* d_v) {
   if (blocks < 1) blocks = 1;
   if (blocks > LVPP_NUM_SMS) blocks = LVPP_NUM_SMS;  // all blocks resident: see k_halo_p2p
   LAUNCH(h, k_halo_p2p, (int)blocks, 256, 0, hp, H.send_nodes, H.recv_nodes, nr, (double2*)d_v, (const double2*)H.rbuf[par],
-         H.flags, H.counters, seq, h->p2p_err);
+         H.flags, H.counters, seq, h->p2p_err, h->halo_timeout_ticks);
   CK(cudaGetLastError());
   return 0;
 }
@@ -338,6 +342,6 @@ extern "C" int lvpp_halo_forward(lvpp_handle h, double* d_v) {
   if (!h || !d_v) { lvpp_set_error("null argument"); return LVPP_E_INVALID; }
   CK(cudaSetDevice(h->device));
   CKR(lvpp_halo_forward_impl(h, d_v));
-  CK(cudaStreamSynchronize(h->stream));
+  CKR(lvpp_sync_check_comm(h));
   return LVPP_OK;
 }

@@ -200,7 +200,7 @@ int lvpp_minres(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_ne
       ++launched;
     }
     CK(cudaMemcpyAsync(h->scal_host, h->scal, sizeof(KryScal), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CKR(lvpp_sync_check_comm(h));
     {
       float sms = 0.f;
       CK(cudaEventElapsedTime(&sms, h->evs0, h->evs1));

@@ -187,6 +187,7 @@ struct lvpp_problem {
   int rank = 0, nranks = 1;
   void* nccl_comm = nullptr;
   int* p2p_err = nullptr;         // pinned, device-visible: set when a peer flag was not raised in time
+  long long halo_timeout_ticks = 1LL << 34;  // clock64 ticks a halo kernel waits for a neighbour (~8 s; LVPP_HALO_TIMEOUT_S)
   LevelHalo halo;                 // fine-level halo (lvpp_obstacle_desc)
   int64_t global_rows = 0;
   // multigrid hierarchy + GMRES workspace (built lazily by lvpp_mg_setup)
@@ -236,6 +237,24 @@ struct lvpp_problem {
   int64_t vcycles = 0;
   int64_t fine_op_launches = 0;
 };
+
+// Synchronise the stream and look at the peer-memory halo's error word (comm.cu: a neighbour's flag that is not raised in
+// time makes k_halo_p2p give up and scatter whatever sits in the receive buffer): every host synchronisation that may
+// follow a halo exchange goes through here, so stale ghosts never reach the caller silently.  The word is cleared so
+// that one failure is reported once.
+static inline int lvpp_sync_check_comm(lvpp_problem* h) {
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) {
+    lvpp_set_error("cudaStreamSynchronize -> %s", cudaGetErrorString(e));
+    return LVPP_E_CUDA;
+  }
+  if (h->p2p_err && *h->p2p_err) {
+    *h->p2p_err = 0;
+    lvpp_set_error("peer-memory halo: a neighbour's flag was not raised in time (LVPP_HALO_TIMEOUT_S, LVPP_HALO=nccl)");
+    return LVPP_E_COMM;
+  }
+  return 0;
+}
 
 template <class T>
 int lvpp_dalloc(lvpp_problem* h, T** p, size_t n, bool zero = true) {

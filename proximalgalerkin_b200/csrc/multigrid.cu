@@ -1219,7 +1219,7 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
     }
     // end of the restart cycle (or of the solve): the state after everything queued so far
     CK(cudaMemcpyAsync(&ring[GM_RING], st, sizeof(GmState), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CKR(lvpp_sync_check_comm(h));
     fin = ring[GM_RING];
     for (int q = polled; q < j; ++q)
       if (q < fin.ncols) CKR(take_samples(q % GM_RING));
@@ -1246,7 +1246,6 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
   }
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaEventSynchronize(h->ev1));
-  if (h->p2p_err && *h->p2p_err) { lvpp_set_error("peer-memory halo: a neighbour's flag was not raised in time"); return LVPP_E_COMM; }
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->t_krylov_ms += ms;

@@ -56,7 +56,7 @@ extern "C" int lvpp_newton_begin(lvpp_handle h, const double* d_x, double* h_fno
   CKR(lvpp_eval_residual(h, d_x, h->F, true));
   CK(cudaMemcpyAsync(h->red_host, h->scal->red, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaEventRecord(h->ev1, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  CKR(lvpp_sync_check_comm(h));
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->t_assembly_ms += ms;
@@ -83,7 +83,7 @@ extern "C" int lvpp_newton_step(lvpp_handle h, double* d_x, const lvpp_newton_op
   CKR(lvpp_eval_residual(h, d_x, h->F, true));  // writes red[0]
   CK(cudaMemcpyAsync(h->red_host, h->scal->red, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaEventRecord(h->ev1, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  CKR(lvpp_sync_check_comm(h));
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->t_assembly_ms += ms;
@@ -138,5 +138,16 @@ extern "C" int lvpp_newton_solve_host(lvpp_handle h, double* h_x, const lvpp_new
     CK(cudaMemcpyAsync(h_x, h->xhost_stage, bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
   }
+  return LVPP_OK;
+}
+
+// The last iterate of lvpp_newton_solve_host whatever its reason: dolfinx.fem.petsc.NonlinearProblem.solve leaves the
+// last Newton iterate in u (obstacle_pg.py:190; the recovery loops of examples 03 / 07 / 08 restore it themselves),
+// while lvpp's SNESSolver.solve writes u only on convergence (src/lvpp/problem.py:121-123).
+extern "C" int lvpp_get_last_iterate_host(lvpp_handle h, double* h_x) {
+  if (!h || !h_x) { lvpp_set_error("null argument"); return LVPP_E_INVALID; }
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(h_x, h->xhost_stage, sizeof(double) * 2 * h->V, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   return LVPP_OK;
 }

@@ -240,6 +240,7 @@ class DeviceProblem:
     def sync_coefficients(self):
         """Read the form's mutable inputs the way a dolfinx assembly would at call time."""
         self.set_alpha(self.F.alpha.value)
+        _capi.check(self.lib.lvpp_set_forcing(self.h, float(self.F.f.value)))
         self.set_previous(self.F.sol_k.x.array)
 
     # -- assembly / linear algebra ---------------------------------------------------------------
@@ -485,7 +486,10 @@ class SNESSolver:
         self._b = None
         self._x = None
 
-    def solve(self):
+    def solve(self, copy_on_failure=False):
+        """``copy_on_failure``: also write the last Newton iterate into ``u`` when SNES did not converge -- what
+        dolfinx.fem.petsc.NonlinearProblem.solve does (NonlinearProblem below passes True); the reference's own
+        SNESSolver.solve only writes ``u`` on convergence (src/lvpp/problem.py:121-123)."""
         dev = self.problem.device_problem
         self.converged_reason, self.iterations, self.linear_iterations = 0, 0, 0  # never report a previous solve
         dev.sync_coefficients()
@@ -501,10 +505,12 @@ class SNESSolver:
                                      maxstep=getattr(o, "linesearch_maxstep", 1e8))
             reason, its = nb.solve(dev.x)
             fnorm, lin = nb.fnorm, nb.linear_its
-            if reason > 0:  # SNESSolver.solve only overwrites the caller's function on convergence (problem.py:121-123)
+            if reason > 0 or copy_on_failure:  # SNESSolver.solve only overwrites the caller's function on convergence (problem.py:121-123)
                 xh[:] = dev.x.numpy()
         else:
             reason, its, fnorm, lin = dev.newton_solve_host(xh, self._opts)  # writes xh only if reason > 0
+            if reason <= 0 and copy_on_failure:
+                _capi.check(dev.lib.lvpp_get_last_iterate_host(dev.h, _capi.as_ptr(xh, C.c_double)))
         self.converged_reason, self.iterations, self.fnorm, self.linear_iterations = reason, its, fnorm, lin
         if _flag(self.options, "snes_monitor"):
             print(f"  SNES: {its} Newton steps, ||F|| = {fnorm:.6e}, {lin} Krylov iterations, reason {reason}")
@@ -574,7 +580,7 @@ class NonlinearProblem:
         return self._problem.device_problem
 
     def solve(self):
-        reason, its = self._snes.solve()
+        reason, its = self._snes.solve(copy_on_failure=True)  # dolfinx leaves the last iterate in u whatever the reason
         if reason == SNES_DIVERGED_LINEAR_SOLVE and _flag(self._options, "ksp_error_if_not_converged"):
             raise NotConvergedError("KSP did not converge (ksp_error_if_not_converged)", reason, its)
         if reason <= 0 and _flag(self._options, "snes_error_if_not_converged"):

@@ -3,11 +3,9 @@ library's assembly / Krylov / J*v entry points) against the oracle's restated PE
 import numpy as np
 import pytest
 
-# Written after the round's last GPU minute: the loop's control flow is checked on the CPU (tests/test_linesearch.py)
-# and every device call it makes is covered by the other GPU tests, but the composition has not run on hardware yet.
-# Non-strict xfail keeps a first-run surprise from masking the rest of the suite (it reports XPASS when it passes);
-# to be made strict in round 2.
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run pending (round 2)")]
+# Plain tests: all of them passed on a B200 in round 2 (profiles/r02_gpu_tests.txt); the blanket non-strict xfail of
+# round 1 is gone.
+pytestmark = [pytest.mark.gpu]
 
 
 def test_obstacle_bt_matches_oracle(lib):
@@ -122,12 +120,12 @@ def test_residual_and_jacobian_at_extreme_latent_values(lib):
     assert np.abs(vals[big] - vo[big]).max() <= 1e-9 * np.abs(vo[big]).max()
 
 
-@pytest.mark.parametrize("env", [{"LVPP_GMRES_WEIGHT": "auto"}, {"LVPP_GMRES_FUSED_NORM": "1"},
-                                 {"LVPP_GMRES_WEIGHT": "auto", "LVPP_GMRES_FUSED_NORM": "1"},
-                                 {"LVPP_GMRES_FLEXIBLE": "1"}, {"LVPP_GMRES_FLEXIBLE": "1", "LVPP_GMRES_WEIGHT": "auto"}])
-def test_experimental_gmres_switches_solve_the_same_system(lib, env, monkeypatch):
-    """The equilibrated residual norm, the one-reduction Gram-Schmidt and flexible GMRES (all off by default) change
-    the Krylov process, not the solution."""
+@pytest.mark.parametrize("env", [{}, {"LVPP_GMRES_WEIGHT": "off"}, {"LVPP_GMRES_FLEXIBLE": "1"},
+                                 {"LVPP_GMRES_FLEXIBLE": "1", "LVPP_GMRES_WEIGHT": "off"}, {"LVPP_GMRES_RESTART": "7"}])
+def test_gmres_switches_solve_the_same_system(lib, env, monkeypatch):
+    """The residual norm (equilibrated by default, Euclidean with LVPP_GMRES_WEIGHT=off), flexible GMRES and the
+    restart length change the Krylov process, not the solution (restart 7: several cycles, the restart path of the
+    device-resident recurrence)."""
     _solve_with_env(env, monkeypatch)
 
 

@@ -3,7 +3,7 @@ proximalgalerkin_b200/recovery.py) against the oracle's restatement of fracture_
 
 CPU tests: the product's driver (obstacle_pg.solve_problem) runs unchanged over a numpy stand-in for the device
 problem, so that its control flow -- which solve counts as failed, what is restored, how alpha moves -- is compared
-with the restated loop attempt by attempt.  The GPU parity test is in tests/test_zz_gpu_linesearch.py.
+with the restated loop attempt by attempt.  The GPU parity test is in tests/test_gpu_linesearch.py.
 """
 import types
 
