@@ -19,6 +19,8 @@ def main():
     ap.add_argument("--size", type=int, default=215)
     ap.add_argument("--nz", type=int, default=None, help="cubes along z over all ranks (default: --size)")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--tol", type=float, default=1e-4, help="tol_exit of the outer loop (CI: 1e-4; script default 1e-6)")
+    ap.add_argument("--alpha-max", dest="alpha_max", type=float, default=1e2)
     ap.add_argument("--pc", default="mg")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--snes-rtol", dest="snes_rtol", type=float, default=None,
@@ -50,7 +52,7 @@ def main():
         opts["snes_rtol"] = args.snes_rtol
     if args.alpha_scheme == "adaptive":  # a failed solve is reported as a reason, not raised
         opts.update({"snes_error_if_not_converged": False, "ksp_error_if_not_converged": False})
-    st = lvpp.obstacle_pg.LvppStepper(msh, 1, args.alpha_scheme, 1e2, 1e-4, petsc_options=opts)
+    st = lvpp.obstacle_pg.LvppStepper(msh, 1, args.alpha_scheme, args.alpha_max, args.tol, max_outer=100, petsc_options=opts)
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t0
     t1 = time.perf_counter()
