@@ -98,14 +98,14 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_newton_steps(n_cpu, steps, warmup, alpha_scheme="constant", alpha_max=1e5, tol_exit=1e-6):
+def cpu_newton_steps(n_cpu, steps, warmup, alpha_scheme="constant", alpha_max=1e5, tol_exit=1e-6, dim=3):
     """Times `steps` Newton steps of the oracle's LVPP solve (after `warmup`) on an n_cpu^3 mesh.
     Returns (DOFs/s, seconds, rows, steps_done)."""
     import numpy as np
 
     from oracle import lvpp_driver, mesh as omesh, obstacle as oobs, snes as osnes
 
-    orc = oobs.ObstacleOracle(omesh.box_kuhn(n_cpu, n_cpu, n_cpu))
+    orc = oobs.ObstacleOracle(omesh.box_kuhn(n_cpu, n_cpu, n_cpu) if dim == 3 else omesh.rectangle(n_cpu, n_cpu))
     import scipy.sparse.linalg as spla
 
     x = np.zeros(orc.num_rows)
@@ -157,15 +157,17 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_cpu = args.n_cpu
-    val, secs, rows, nsteps = cpu_newton_steps(n_cpu, args.steps, args.warmup, args.alpha_scheme, args.alpha_max, args.tol_exit)
-    sample = (f"{nsteps} Newton steps of the same LVPP obstacle solve on a {n_cpu}^3-cube Kuhn mesh ({rows} rows), "
+    dim = 2 if args.workload == "obstacle2d" else 3
+    n_cpu = args.n_cpu if dim == 3 else max(args.n_cpu, 150)
+    val, secs, rows, nsteps = cpu_newton_steps(n_cpu, args.steps, args.warmup, args.alpha_scheme, args.alpha_max, args.tol_exit, dim)
+    sample = (f"{nsteps} Newton steps of the same LVPP obstacle solve on a {n_cpu}^{dim} " + ("cube Kuhn" if dim == 3 else "square right-diagonal") + f" mesh ({rows} rows), "
               f"numpy assembly + scipy SuperLU (stand-in for dolfinx + MUMPS; sequential factorisation, {blas_threads()} BLAS threads)")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": nsteps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(nsteps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"3-D P1 obstacle LVPP, CPU sample n={n_cpu} ({rows} rows); GPU arm runs n={args.n} per GPU"},
+        "config": {"workload": f"{dim}-D P1 obstacle LVPP, CPU sample n={n_cpu} ({rows} rows); GPU arm runs n={args.n if dim == 3 else args.n2d} per GPU",
+                   "alpha_scheme": args.alpha_scheme, "alpha_max": args.alpha_max, "tol_exit": args.tol_exit},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": blas_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "newton_steps_per_sec": nsteps / secs,
@@ -210,8 +212,17 @@ def run_b200(args):
     # into N z-slabs.  "stack": N copies of the n^3 problem stacked along z on [-1,1]^2 x [-N,N] with one obstacle
     # per slab (the far slabs of a single obstacle see phi = -16 and the first Newton step from psi = 0 overshoots
     # past PETSc's divergence tolerance).  --slabs S emulates the S-GPU "stack" problem on one GPU (diagnostic).
-    nxy, nz, lo, hi, slabs = weak_scaling_mesh(n, world, args.weak, args.slabs)
-    msh = lvpp.mesh.create_box(nxy, nxy, nz, lo=lo, hi=hi, rank=rank, nranks=world)
+    dim = 2 if args.workload == "obstacle2d" else 3
+    if dim == 2:
+        # configs[0]: the 2-D obstacle problem of examples/01 on the unit square mapped to [-1,1]^2, N x N squares with
+        # the right diagonal (N = 1000: 2 004 002 rows); N GPUs: N sqrt(world) squares per axis, y-slabs
+        n = args.n2d
+        nxy = int(round(n * world ** 0.5))
+        nz, slabs = world * max(1, int(round(nxy / world))), 1
+        msh = lvpp.mesh.create_rectangle(nxy, nz, rank=rank, nranks=world)
+    else:
+        nxy, nz, lo, hi, slabs = weak_scaling_mesh(n, world, args.weak, args.slabs)
+        msh = lvpp.mesh.create_box(nxy, nxy, nz, lo=lo, hi=hi, rank=rank, nranks=world)
     opts = {"ksp_rtol": args.ksp_rtol, "ksp_max_it": 200000}
     if args.pc == "mg":
         opts = {"ksp_rtol": args.ksp_rtol, "ksp_type": "gmres", "pc_type": "mg", "ksp_max_it": 400}
@@ -314,15 +325,15 @@ def run_b200(args):
     roof_extra = None
     if n_p:
         sm_ms = (s1["smooth_sampled_ms"] - s0["smooth_sampled_ms"]) / n_p
-        # (LVPP_MG_PACK=bf16, experimental: 20-byte records per pair of slots, kernel k_packed2_op)
-        rec = 10 if os.environ.get("LVPP_MG_PACK") == "bf16" and os.environ.get("LVPP_MG_FP32", "1") != "0" else 16
+        # (bf16 pair records, 20 bytes per pair of slots, kernel k_packed2_op; LVPP_MG_PACK=fp32: 16-byte records, k_packed_op)
+        rec = 10 if os.environ.get("LVPP_MG_PACK", "bf16") != "fp32" and os.environ.get("LVPP_MG_FP32", "1") != "0" else 16
         sm_bytes = rec * slots + (16 + 16 + (16 if rec == 10 else 32) + 16 + 1 + 0.25) * V_own
         roofline = {
             "bound": "hbm", "kernel": ("k_packed2_op (multigrid smoother sweep on the fine level: bf16 pair records, 10 B / slot, " if rec == 10 else
                                        "k_packed_op (multigrid smoother sweep on the fine level: packed {col, alpha K, M, D} "
                                        "single-precision records, ") + "fp64 accumulation, fused node-block Jacobi update)",
             "achieved": sm_bytes / (sm_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": sm_bytes / (sm_ms * 1e-3) / 1e9 / peak,
-            "traffic": traffic_of("smooth_traffic.json") if rec == 16 else None, "peak_source": peak_src, "frac_of_nominal_8tbs": sm_bytes / (sm_ms * 1e-3) / 1e9 / 8000.0,
+            "traffic": traffic_of("smooth_traffic.json" if rec == 16 else "smooth_traffic_bf16.json"), "peak_source": peak_src, "frac_of_nominal_8tbs": sm_bytes / (sm_ms * 1e-3) / 1e9 / 8000.0,
             "algorithmic_bytes_per_launch": sm_bytes,
             "ms_per_launch": sm_ms, "launches_sampled": n_p, "launches_in_timed_region": packed_ops,
             "share_of_step": sm_ms * packed_ops / (secs * 1e3) if secs > 0 else None,
@@ -386,9 +397,10 @@ def run_b200(args):
     # ---- CPU baseline on this box's host cores (bounded sample)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        val, secs_c, rows_c, ns = cpu_newton_steps(args.n_cpu, 5, 1, args.alpha_scheme, args.alpha_max, args.tol_exit)
+        n_cpu = args.n_cpu if dim == 3 else max(args.n_cpu, 150)
+        val, secs_c, rows_c, ns = cpu_newton_steps(n_cpu, 5, 1, args.alpha_scheme, args.alpha_max, args.tol_exit, dim)
         cpu = {"value": val, "unit": UNIT, "cores": blas_threads(), "kind": "port",
-               "sample": f"{ns} Newton steps of the same LVPP solve on a {args.n_cpu}^3-cube Kuhn mesh ({rows_c} rows), "
+               "sample": f"{ns} Newton steps of the same LVPP solve on a {n_cpu}^{dim} structured mesh ({rows_c} rows), "
                          f"numpy assembly + SuperLU (oracle/; sequential factorisation, threaded BLAS), {secs_c:.1f} s; "
                          f"host has {os.cpu_count()} cores"}
         if not args.no_aux:
@@ -405,15 +417,17 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": done, "warmup": args.warmup,
             "ms_per_step": 1e3 * secs / max(done, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"3-D P1 obstacle LVPP (configs[1]): {nxy}x{nxy}x{nz} cubes x 6 tets, "
+            "config": {"workload": (f"3-D P1 obstacle LVPP (configs[1]): {nxy}x{nxy}x{nz} cubes x 6 tets, " if dim == 3 else
+                                    f"2-D P1 obstacle LVPP (configs[0], examples/01): {nxy}x{nz} squares x 2 triangles on [-1,1]^2, ") +
                                    f"{rows_global} rows, {stats0['nnz']} nnz/GPU (CSR-equivalent)",
                        "n": n, "rows": rows_global, "primal_dofs": rows_global // 2,  # the reference's CSV column "dofs" (obstacle_pg.py:237,255)
                        "alpha_scheme": args.alpha_scheme, "alpha_max": args.alpha_max, "tol_exit": args.tol_exit, "max_outer": 100,
                        "schedule_note": SCHEDULE_NOTE, "snes_linesearch_type": "none", "snes_rtol": 1e-6, "ksp": ("MINRES + block-Jacobi/Schur-diag" if args.pc == "jacobi" else
                                "GMRES(50) + monolithic aggregation multigrid V(2,2) (node-block Jacobi sweeps with Chebyshev-root "
-                               "dampings, ratio 6; packed single-precision cycle operator, fp64 Krylov operator)"), "ksp_rtol": args.ksp_rtol,
-                       "l2": "operator (>=4 GB) and vectors exceed the 126 MB L2; no flush needed" if n >= 100 else
-                             "inputs fit L2: kernel-level numbers are L2-warm",
+                               "dampings, ratio 6; cycle operator from packed bf16 pair records with fp64 accumulation, fp64 Krylov operator)"), "ksp_rtol": args.ksp_rtol,
+                       "l2": "operator (>=4 GB) and vectors exceed the 126 MB L2; no flush needed" if (dim == 3 and n >= 100) else
+                             ("operator (0.6 GB at N = 1000) and Krylov basis exceed the 126 MB L2; no flush" if dim == 2 and n >= 700 else
+                              "inputs fit L2: kernel-level numbers are L2-warm"),
                        "parallelism": f"slab{world}", "weak_scaling": (None if world == 1 else args.weak),
                        "obstacle": "phi_set of obstacle_pg.py:92-104" + (", one copy per slab (period 2 in z)" if slabs > 1 else "")},
             "newton_steps_per_sec": done / secs, "krylov_iterations": kry, "vcycles": s1["vcycles"] - s0["vcycles"],
@@ -505,8 +519,10 @@ def main():
     ap.add_argument("--ksp-rtol", dest="ksp_rtol", type=float, default=1e-12)
     ap.add_argument("--pc", default="mg", choices=["jacobi", "mg"],
                     help="jacobi: block-diagonal MINRES; mg: multigrid-preconditioned GMRES")
-    ap.add_argument("--workload", default="obstacle", choices=["obstacle", "gradient", "multiphase", "signorini"],
-                    help="obstacle (the driver's line, configs[1]) or one of the mixed-form examples (1 GPU, --size = N)")
+    ap.add_argument("--workload", default="obstacle", choices=["obstacle", "obstacle2d", "gradient", "multiphase", "signorini"],
+                    help="obstacle (the driver's line, configs[1]), obstacle2d (configs[0]: the 2-D problem of examples/01, "
+                         "--size2d squares per axis) or one of the mixed-form examples (1 GPU, --size = N)")
+    ap.add_argument("--size2d", dest="n2d", type=int, default=1000, help="obstacle2d: squares per axis (1000: 2 004 002 rows)")
     ap.add_argument("--alpha-scheme", dest="alpha_scheme", default="constant", choices=["constant", "double_exponential", "geometric"],
                     help="obstacle_pg.py --alpha-scheme (its default: constant)")
     ap.add_argument("--alpha-max", dest="alpha_max", type=float, default=1e5, help="obstacle_pg.py --alpha-max (default 1e5)")
@@ -522,7 +538,7 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload != "obstacle":
+    elif args.workload not in ("obstacle", "obstacle2d"):
         run_forms(args)
     else:
         run_b200(args)

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256, MINB) k_packed_op(PackedOpArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Experimental (LVPP_MG_PACK=bf16, off by default): bf16 values, one record per PAIR of consecutive slots of a row --
+// The default records of the cycle (LVPP_MG_PACK=fp32 selects the ones above): bf16 values, one record per PAIR of consecutive slots of a row --
 // a 128-bit load {col0, col1, bf16(alpha K0)|bf16(M0), bf16(alpha K1)|bf16(M1)} and a 32-bit load bf16(D0)|bf16(D1):
 // 10 instead of 16 bytes per slot, and the node-block inverses in single precision (16 instead of 32 bytes per node):
 // the fine-level sweep at n = 215 moves 2.15 instead of 3.22 GB.  bf16 keeps the exponent range

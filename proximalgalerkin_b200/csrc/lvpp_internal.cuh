@@ -93,7 +93,7 @@ struct MgLevel {
   uint8_t* diag_k = nullptr;
   double *K = nullptr, *M = nullptr, *D = nullptr;
   uint4* P = nullptr;            // packed single-precision copy {col, alpha K, M, D} read by the cycle (block_op.cuh)
-  // experimental bf16 copy (LVPP_MG_PACK=bf16): one record per PAIR of slots, 20 bytes (block_op.cuh: k_packed2_op)
+  // bf16 copy (the default; LVPP_MG_PACK=fp32 for the records above): one record per PAIR of slots, 20 bytes (block_op.cuh: k_packed2_op)
   uint4* P2 = nullptr;           // {col0, col1, bf16(alpha K0) | bf16(M0), bf16(alpha K1) | bf16(M1)}
   uint32_t* Pd = nullptr;        // bf16(D0) | bf16(D1)
   float4* binv32 = nullptr;      // [Vown] single-precision copy of binv for k_packed2_op
@@ -207,7 +207,7 @@ struct lvpp_problem {
   int32_t mg_best_its = 0;        // fewest Krylov iterations of a converged solve on this handle (adaptive Chebyshev ratio)
   int64_t mg_retries = 0;         // Krylov solves repeated after a re-estimate
   int mg_unroll = 4;              // slots per register buffer of k_packed_op (4 or 8)
-  bool mg_bf16 = false;           // experimental: bf16 pair records instead of the single-precision ones (10 B / slot)
+  bool mg_bf16 = true;            // bf16 pair records (10 B / slot) instead of the single-precision ones (16 B / slot)
   double mg_cheb = 6.0;           // > 1: Chebyshev-root damping of the sweeps over [b / mg_cheb, b]; else plain damping
   double mg_alpha_est = -1.0;     // alpha of the last smoother eigenvalue estimate
   double* coarse_lu = nullptr;    // dense inverse of the coarsest operator (all ranks' rows) [nc * nc]

@@ -743,7 +743,11 @@ int lvpp_mg_setup(lvpp_problem* h) {
     if (stop) break;
   }
   h->mg_fp32 = env_double("LVPP_MG_FP32", 1.0) != 0.0;
-  if (const char* pk = getenv("LVPP_MG_PACK")) h->mg_bf16 = h->mg_fp32 && strcmp(pk, "bf16") == 0;
+  // records of the cycle's operator copy: bf16 pairs (10 bytes per slot; the default from round 2: same Newton and
+  // Krylov counts as the single-precision records over the whole n = 215 solve, 15 % less time --
+  // profiles/r02_scan_const_alpha.txt) or LVPP_MG_PACK=fp32 (16 bytes per slot)
+  h->mg_bf16 = h->mg_fp32;
+  if (const char* pk = getenv("LVPP_MG_PACK")) h->mg_bf16 = h->mg_fp32 && strcmp(pk, "fp32") != 0;
   if (h->mg_fp32)
     for (size_t l = 0; l + 1 < h->levels.size(); ++l) {
       MgLevel& L = h->levels[l];

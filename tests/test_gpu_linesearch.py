@@ -121,10 +121,10 @@ def test_residual_and_jacobian_at_extreme_latent_values(lib):
 
 
 @pytest.mark.parametrize("env", [{}, {"LVPP_GMRES_WEIGHT": "off"}, {"LVPP_GMRES_FLEXIBLE": "1"},
-                                 {"LVPP_GMRES_FLEXIBLE": "1", "LVPP_GMRES_WEIGHT": "off"}, {"LVPP_GMRES_RESTART": "7"}])
+                                 {"LVPP_GMRES_FLEXIBLE": "1", "LVPP_GMRES_WEIGHT": "off"}, {"LVPP_GMRES_RESTART": "20"}])
 def test_gmres_switches_solve_the_same_system(lib, env, monkeypatch):
     """The residual norm (equilibrated by default, Euclidean with LVPP_GMRES_WEIGHT=off), flexible GMRES and the
-    restart length change the Krylov process, not the solution (restart 7: several cycles, the restart path of the
+    restart length change the Krylov process, not the solution (restart 20: several cycles, the restart path of the
     device-resident recurrence)."""
     _solve_with_env(env, monkeypatch)
 
@@ -245,9 +245,10 @@ def test_device_path_against_reference_style_export(lib, case):
         assert np.linalg.norm(uf - g["u_final"]) <= 1e-10 * np.linalg.norm(g["u_final"])
 
 
-@pytest.mark.parametrize("env", [{"LVPP_MG_PACK": "bf16"}, {"LVPP_MG_PACK": "bf16", "LVPP_MG_UNROLL": "8"}])
-def test_zz_bf16_pair_records_precondition_the_same_system(lib, env, monkeypatch):
-    """LVPP_MG_PACK=bf16 (off by default; block_op.cuh:k_packed2_op): the cycle reads bf16 pair records and
-    single-precision block inverses -- a different preconditioner, the same solution.  Last in the file: a kernel that
-    has never run on hardware goes after everything else."""
+@pytest.mark.parametrize("env", [{"LVPP_MG_PACK": "bf16"}, {"LVPP_MG_PACK": "bf16", "LVPP_MG_UNROLL": "8"}, {"LVPP_MG_PACK": "fp32"},
+                                 {"LVPP_MG_PACK": "fp32", "LVPP_MG_UNROLL": "8"}, {"LVPP_MG_FP32": "0"}])
+def test_cycle_record_formats_precondition_the_same_system(lib, env, monkeypatch):
+    """The cycle's copy of the operator: bf16 pair records + single-precision block inverses (the default,
+    block_op.cuh:k_packed2_op), single-precision records (LVPP_MG_PACK=fp32, k_packed_op) or the fp64 operator itself
+    (LVPP_MG_FP32=0) -- different preconditioners, the same solution."""
     _solve_with_env(env, monkeypatch)

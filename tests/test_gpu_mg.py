@@ -2,6 +2,7 @@
 sparse LU, and full LVPP solves with identical Newton / proximal iteration counts."""
 import numpy as np
 import pytest
+import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 pytestmark = pytest.mark.gpu
@@ -96,3 +97,36 @@ def test_mg_variants_solve_the_same_system(lib, env, monkeypatch):
     assert reason > 0 and its < 80, (its, reason)
     ye = spla.splu(orc.jacobian(x, 3.0).tocsc()).solve(rhs)
     assert np.linalg.norm(Y.numpy() - ye) / np.linalg.norm(ye) < 1e-8
+
+
+@pytest.mark.parametrize("kind,n", [("tri", 128), ("tet", 32)])
+def test_mid_solve_linear_solve_matches_host_lu_on_both_row_blocks(lib, kind, n):
+    """After two proximal steps the contact set has formed (psi down to -20, D = int exp(psi) phi_i phi_j ~ 0 on it): the
+    Krylov solution of the Newton system at that state agrees with a host sparse LU of the exported CSR on the u block AND
+    on the psi block, and the true residual is small in both blocks (round-1 verdict: a stopping test that is blind to
+    the psi rows would pass the first and fail the second)."""
+    lvpp, s, dev, orc = _pair(kind, n, 1)
+    st = lvpp.obstacle_pg.LvppStepper(s["V"].mesh, 1, "double_exponential", 1e2, 1e-4, petsc_options=MG, setup_objects=s)
+    while st.k < 2 and st.step():
+        pass
+    assert st.k == 2 and st.history["newton_steps"][0] >= 4
+    x = st.x.numpy()
+    assert x[1::2].min() < -8.0  # a developed contact set
+    rng = np.random.default_rng(5)
+    X, R, Y, JY = (lvpp.DeviceVector(dev.n, dev.device) for _ in range(4))
+    X.set(x)
+    fn = dev.assemble_residual(X, R)  # the right-hand side of the next Newton step; leaves the Jacobian at x assembled
+    assert fn > 0
+    its, reason, _ = dev.linear_solve(R, Y, lvpp.newton_options(dict(MG, ksp_rtol=1e-12)))
+    assert reason > 0 and its < 100, (its, reason)
+    indptr, indices = dev.csr_pattern()
+    J = sp.csr_matrix((dev.jacobian_values().cpu().numpy(), indices, indptr), shape=(dev.n, dev.n))
+    rhs, y = R.numpy(), Y.numpy()
+    ye = spla.splu(J.tocsc()).solve(rhs)
+    for blk, name in ((slice(0, None, 2), "u"), (slice(1, None, 2), "psi")):
+        err = np.linalg.norm(y[blk] - ye[blk]) / np.linalg.norm(ye[blk])
+        assert err < 1e-8, (name, err)
+    r = J @ y - rhs
+    scale_u, scale_p = np.abs(J[0::2]).sum(axis=1).max(), np.abs(J[1::2]).sum(axis=1).max()  # row scales of the two blocks
+    assert np.linalg.norm(r[0::2]) <= 1e-9 * scale_u * np.linalg.norm(y) / np.sqrt(y.size)
+    assert np.linalg.norm(r[1::2]) <= 1e-9 * scale_p * np.linalg.norm(y) / np.sqrt(y.size)
