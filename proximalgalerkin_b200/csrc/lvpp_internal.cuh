@@ -201,6 +201,7 @@ struct lvpp_problem {
   // over-correction of the piecewise-constant coarse correction and relative damping of the smoother
   // (omega_l = mg_omega * 2 / (1.15 lambda_max)); tuned on the n = 215 obstacle problem (profiles/r01_mg_scan.txt)
   double mg_omega = 1.0, mg_over = 1.8;
+  double mg_kscale = 1.0;         // coarse stiffness divided by this at every coarsening (multigrid.cu: build_next_level)
   double mg_margin = 1.10;        // safety factor on the power-iteration estimate of lambda_max(Binv J)
   int mg_power_its = 10;
   int mg_power_boost = 1;         // multiplier of the power iterations (10 while re-estimating after a failed solve)

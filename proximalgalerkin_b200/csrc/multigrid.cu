@@ -166,7 +166,7 @@ __global__ void k_coarse_cols(int64_t Vc, const int64_t* __restrict__ rowstart, 
 // Galerkin sums through the sorted slot map: Xc[dst[u]] = sum_{p in seg(u)} X[src[p]] (fixed order)
 __global__ void k_galerkin(int64_t nnzc, const int64_t* __restrict__ gal_ptr, const uint32_t* __restrict__ gal_src,
                            const int64_t* __restrict__ gal_dst, int narr, const double* __restrict__ X0,
-                           const double* __restrict__ X1, double* __restrict__ Y0, double* __restrict__ Y1) {
+                           const double* __restrict__ X1, double* __restrict__ Y0, double* __restrict__ Y1, double scale0) {
   for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < nnzc; u += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p1 = gal_ptr[u + 1];
     double a0 = 0.0, a1 = 0.0;
@@ -176,7 +176,7 @@ __global__ void k_galerkin(int64_t nnzc, const int64_t* __restrict__ gal_ptr, co
       if (narr > 1) a1 += X1[s];
     }
     const int64_t d = gal_dst[u];
-    Y0[d] = a0;
+    Y0[d] = a0 * scale0;
     if (narr > 1) Y1[d] = a1;
   }
 }
@@ -641,7 +641,13 @@ static int build_next_level(lvpp_problem* h, int l, bool* stop) {
          C.diag_k, F.gal_dst);
   CK(cudaGetLastError());
   // constant operators of the coarse level
-  LAUNCH(h, k_galerkin, lvpp_grid(nnzc, 256, 16), 256, 0, nnzc, F.gal_ptr, F.gal_src, F.gal_dst, 2, F.K, F.M, C.K, C.M);
+  // The Galerkin stiffness of a piecewise-constant prolongation over-estimates the energy of smooth functions by about
+  // the aggregate width (2 per coarsening): K_c is divided by mg_kscale here, level after level, instead of (or
+  // together with) multiplying the coarse correction by mg_over.  The two are the same thing for the elliptic block of a
+  // two-level method; on the contact set, where the roles of the blocks are exchanged (psi_c = M_c^-1 (r - alpha K_c u_c)),
+  // only the rescaled stiffness gives a coarse correction of the right size.  M_c and D_c are exact for constants.
+  LAUNCH(h, k_galerkin, lvpp_grid(nnzc, 256, 16), 256, 0, nnzc, F.gal_ptr, F.gal_src, F.gal_dst, 2, F.K, F.M, C.K, C.M,
+         1.0 / h->mg_kscale);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   for (void* p : {(void*)keys, (void*)skeys, (void*)vals, tmp, stmp, (void*)ukeys, (void*)rowstart, (void*)d_err,
@@ -662,6 +668,8 @@ int lvpp_mg_setup(lvpp_problem* h) {
   if (h->nranks > 64) { lvpp_set_error("multigrid preconditioner: more than 64 ranks"); return LVPP_E_INVALID; }
   // tunables (defaults are the tested values)
   h->mg_over = env_double("LVPP_MG_OVER", h->mg_over);
+  h->mg_kscale = env_double("LVPP_MG_KSCALE", h->mg_kscale);
+  if (!(h->mg_kscale > 0.0)) { lvpp_set_error("bad LVPP_MG_KSCALE"); return LVPP_E_INVALID; }
   h->mg_omega = env_double("LVPP_MG_OMEGA", h->mg_omega);
   h->mg_nsmooth = (int)env_double("LVPP_MG_NSMOOTH", h->mg_nsmooth);
   if (h->mg_nsmooth < 1 || h->mg_nsmooth > MG_MAX_SWEEPS) { lvpp_set_error("bad LVPP_MG_NSMOOTH"); return LVPP_E_INVALID; }
@@ -926,7 +934,7 @@ int lvpp_mg_update(lvpp_problem* h) {
   for (int l = 0; l + 1 < nl; ++l) {
     MgLevel& F = h->levels[l];
     MgLevel& C = h->levels[l + 1];
-    LAUNCH(h, k_galerkin, lvpp_grid(C.nnz, 256, 16), 256, 0, C.nnz, F.gal_ptr, F.gal_src, F.gal_dst, 1, F.D, F.D, C.D, C.D);
+    LAUNCH(h, k_galerkin, lvpp_grid(C.nnz, 256, 16), 256, 0, C.nnz, F.gal_ptr, F.gal_src, F.gal_dst, 1, F.D, F.D, C.D, C.D, 1.0);
     CK(cudaGetLastError());
   }
   if (h->mg_fp32)

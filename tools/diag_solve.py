@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--max-newton", dest="max_newton", type=int, default=30)
     ap.add_argument("--tol-exit", dest="tol_exit", type=float, default=1e-4)
     ap.add_argument("--alpha-max", dest="alpha_max", type=float, default=1e2)
+    ap.add_argument("--alpha-scheme", dest="alpha_scheme", default="double_exponential")
     ap.add_argument("--lu", action="store_true", help="also solve every system with host sparse LU (small sizes only)")
     args = ap.parse_args()
     import numpy as np
@@ -59,7 +60,7 @@ def main():
     t1 = time.perf_counter()
     total_newton = total_krylov = 0
     for k in range(args.max_outer):
-        alpha, alpha_k = alpha_update("double_exponential", k, alpha, alpha_k, args.alpha_max)
+        alpha, alpha_k = alpha_update(args.alpha_scheme, k, alpha, alpha_k, args.alpha_max)
         dev.set_alpha(alpha)
         dev.set_previous(xk)
         fnorm0 = fnorm = dev.assemble_residual(x, F)
@@ -90,9 +91,10 @@ def main():
             total_newton += 1
             total_krylov += kits
             psi = x.tensor[1:nown:2]
+            npos = int((psi > 1.0).sum())
             print(f"outer {k} alpha {alpha:.4g} newton {its}: |F| {fnorm:.3e} krylov {kits} ({kreason}) "
                   f"rhs u/psi {fu:.2e}/{fp:.2e} lin.res u/psi {ru:.2e}/{rp:.2e} |y| u/psi {yu:.2e}/{yp:.2e} "
-                  f"psi [{float(psi.min()):.4g}, {float(psi.max()):.4g}]{extra}", file=sys.stderr, flush=True)
+                  f"psi [{float(psi.min()):.4g}, {float(psi.max()):.4g}] #psi>1: {npos}{extra}", file=sys.stderr, flush=True)
             if not np.isfinite(fnorm):
                 reason = -4
             elif kreason < 0:
