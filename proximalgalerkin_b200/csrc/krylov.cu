@@ -239,7 +239,7 @@ int lvpp_solve_linear(lvpp_problem* h, const double* d_rhs, double* d_y, const l
     // no ratio is uniformly safe there.  So: start with the default ratio and fall back to plain damping, for the
     // rest of the handle's life, the first time a solve needs 1.5 times the best count seen.  Deterministic;
     // identical on every rank.
-    if (h->mg_cheb > 1.0 && reason1 > 0 && its1 >= 8) {  // (a solve that converges at once says nothing)
+    if (h->mg_cheb_adapt && h->mg_cheb > 1.0 && reason1 > 0 && its1 >= 8) {  // (a solve that converges at once says nothing)
       if (h->mg_best_its == 0 || its1 < h->mg_best_its) h->mg_best_its = its1;
       else if (2 * its1 > 3 * h->mg_best_its && its1 > h->mg_best_its + 8) {
         h->mg_cheb = 0.0;

@@ -209,6 +209,7 @@ struct lvpp_problem {
   int64_t mg_retries = 0;         // Krylov solves repeated after a re-estimate
   int mg_unroll = 4;              // slots per register buffer of k_packed_op (4 or 8)
   bool mg_bf16 = true;            // bf16 pair records (10 B / slot) instead of the single-precision ones (16 B / slot)
+  bool mg_cheb_adapt = false;     // LVPP_MG_CHEB_ADAPT=1: fall back to plain damping once a solve needs 1.5x the best count (krylov.cu)
   double mg_cheb = 6.0;           // > 1: Chebyshev-root damping of the sweeps over [b / mg_cheb, b]; else plain damping
   double mg_alpha_est = -1.0;     // alpha of the last smoother eigenvalue estimate
   double* coarse_lu = nullptr;    // dense inverse of the coarsest operator (all ranks' rows) [nc * nc]

@@ -680,6 +680,7 @@ int lvpp_mg_setup(lvpp_problem* h) {
     return LVPP_E_INVALID;
   }
   h->mg_cheb = env_double("LVPP_MG_CHEB", h->mg_cheb);
+  h->mg_cheb_adapt = env_double("LVPP_MG_CHEB_ADAPT", 0.0) != 0.0;
   h->mg_unroll = (int)env_double("LVPP_MG_UNROLL", h->mg_unroll);
   h->mg_margin = env_double("LVPP_MG_MARGIN", h->mg_margin);
   h->mg_power_its = (int)env_double("LVPP_MG_POWER_ITS", h->mg_power_its);
