@@ -207,11 +207,14 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n = args.n
     t_setup = time.perf_counter()
-    # Weak scaling (N > 1).  "refine" (default): the reference's problem -- one obstacle on [-1,1]^3 -- on a mesh
-    # refined so that every GPU keeps ~n^3 cubes: nx = ny = round(n N^(1/3)), nz = the multiple of 2N nearest to nx, cut
-    # into N z-slabs.  "stack": N copies of the n^3 problem stacked along z on [-1,1]^2 x [-N,N] with one obstacle
-    # per slab (the far slabs of a single obstacle see phi = -16 and the first Newton step from psi = 0 overshoots
-    # past PETSc's divergence tolerance).  --slabs S emulates the S-GPU "stack" problem on one GPU (diagnostic).
+    # Weak scaling (N > 1).  "stack" (default, SURVEY 8d "weak-scaled by stacking slabs in z"): N copies of the n^3
+    # problem stacked along z on [-1,1]^2 x [-N,N], one z-slab and one copy of the obstacle per GPU (a single obstacle
+    # would leave the far slabs at phi = -16, where the first Newton step from psi = 0 overshoots past PETSc's divergence
+    # tolerance).  The mesh width stays 2 / n, so the Newton iteration behaves as on one GPU -- the full Newton step
+    # of the reference stops converging on finer meshes (profiles/r02_newton_robustness.md), which rules out
+    # "refine": one obstacle on [-1,1]^3 on a mesh refined so that every GPU keeps ~n^3 cubes (nx = ny =
+    # round(n N^(1/3)), nz = the multiple of 2N nearest to nx, N z-slabs).  --slabs S emulates the S-GPU "stack"
+    # problem on one GPU (diagnostic).
     dim = 2 if args.workload == "obstacle2d" else 3
     if dim == 2:
         # configs[0]: the 2-D obstacle problem of examples/01 on the unit square mapped to [-1,1]^2, N x N squares with
@@ -423,7 +426,7 @@ def run_b200(args):
                        "n": n, "rows": rows_global, "primal_dofs": rows_global // 2,  # the reference's CSV column "dofs" (obstacle_pg.py:237,255)
                        "alpha_scheme": args.alpha_scheme, "alpha_max": args.alpha_max, "tol_exit": args.tol_exit, "max_outer": 100,
                        "schedule_note": SCHEDULE_NOTE, "snes_linesearch_type": "none", "snes_rtol": 1e-6, "ksp": ("MINRES + block-Jacobi/Schur-diag" if args.pc == "jacobi" else
-                               "GMRES(50) + monolithic aggregation multigrid V(2,2) (node-block Jacobi sweeps with Chebyshev-root "
+                               "GMRES(50) + monolithic aggregation multigrid V(2,3) (node-block Jacobi sweeps with Chebyshev-root "
                                "dampings, ratio 6; cycle operator from packed bf16 pair records with fp64 accumulation, fp64 Krylov operator)"), "ksp_rtol": args.ksp_rtol,
                        "l2": "operator (>=4 GB) and vectors exceed the 126 MB L2; no flush needed" if (dim == 3 and n >= 100) else
                              ("operator (0.6 GB at N = 1000) and Krylov basis exceed the 126 MB L2; no flush" if dim == 2 and n >= 700 else
@@ -527,8 +530,10 @@ def main():
                     help="obstacle_pg.py --alpha-scheme (its default: constant)")
     ap.add_argument("--alpha-max", dest="alpha_max", type=float, default=1e5, help="obstacle_pg.py --alpha-max (default 1e5)")
     ap.add_argument("--tol", dest="tol_exit", type=float, default=1e-6, help="obstacle_pg.py --tol (default 1e-6)")
-    ap.add_argument("--weak", default="refine", choices=["refine", "stack"],
-                    help="N > 1: refine the mesh of the one-obstacle problem (default) or stack N copies along z")
+    ap.add_argument("--weak", default="stack", choices=["refine", "stack"],
+                    help="N > 1: stack N copies of the n^3 problem along z (default; SURVEY 8d: 215 x 215 x 1720 cubes at 8 GPUs, "
+                         "the mesh width -- and with it the behaviour of the full Newton step -- stays that of one GPU) or "
+                         "refine the mesh of the one-obstacle problem")
     ap.add_argument("--slabs", type=int, default=1, help="1 GPU only: solve the global problem of an S-GPU run (diagnostic)")
     ap.add_argument("--skip-e2e", dest="no_e2e", action="store_true")
     ap.add_argument("--skip-cpu", dest="no_cpu", action="store_true")

@@ -196,7 +196,10 @@ struct lvpp_problem {
   double h0 = 0.0;                // node spacing used by the coordinate aggregation
   double xmin[3] = {0, 0, 0};
   int mg_nsmooth = 2;
-  int mg_npre = 2, mg_npost = 2;  // sweeps before / after the coarse-grid correction (LVPP_MG_NSMOOTH sets both)
+  // sweeps before / after the coarse-grid correction (LVPP_MG_NPRE / LVPP_MG_NPOST; LVPP_MG_NSMOOTH sets both).  V(2,3) with
+  // the Chebyshev-root dampings kept for the whole solve: 21 Krylov iterations per Newton step late in the n = 215 solve
+  // against 26 for V(2,2), 4.96 s against 6.05 s for the 37 Newton steps (profiles/r02_cycle_shape_scan.txt)
+  int mg_npre = 2, mg_npost = 3;
   bool mg_fp32 = true;            // the cycle reads the packed single-precision copy of the operator
   // over-correction of the piecewise-constant coarse correction and relative damping of the smoother
   // (omega_l = mg_omega * 2 / (1.15 lambda_max)); tuned on the n = 215 obstacle problem (profiles/r01_mg_scan.txt)
