@@ -413,6 +413,9 @@ def run_b200(args):
                 from oracle import cpu_kernels
 
                 cpu["kernels"] = cpu_kernels.time_kernels(40)
+                # ... and the whole Krylov path: Newton steps with C + OpenMP assembly and
+                # diagonally preconditioned MINRES on the monolithic CSR, all host threads (GPU counterpart: --pc jacobi)
+                cpu["krylov_path"] = cpu_kernels.time_newton_steps_krylov(48 if dim == 3 else 24, 3)
             except Exception as e:  # the baseline library is optional infrastructure
                 cpu["kernels"] = {"unavailable": str(e)[:200]}
     if rank == 0:

@@ -98,3 +98,94 @@ void lvpp_cpu_csr_spmv(int64_t n, const int64_t* indptr, const int32_t* indices,
     y[i] = s;
   }
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * lvpp_cpu_minres: the Krylov solve the north star puts in place of the reference's MUMPS LU (KSP preonly + PC lu,
+ * examples/01_obstacle_problem/obstacle_pg.py:129-131), restated on the CPU for a like-for-like baseline on all host
+ * cores: preconditioned MINRES (Paige & Saunders 1975; the recurrences as in Choi, Paige & Saunders' MINRES-QLP
+ * report, section 2) on the assembled monolithic CSR with a positive diagonal preconditioner -- the recipe of
+ * examples/09_eikonal/ex40.cpp:261-274 reduced to its diagonals: 1 / (alpha K_ii) on the u rows and
+ * 1 / (D_ii + M_ii^2 / (alpha K_ii)) on the psi rows (passed in as pinv).  Stops on the preconditioned residual norm
+ * <= rtol * initial.  Returns the iteration count; y0 = 0. */
+static double dot_omp(int64_t n, const double* a, const double* b) {
+  double s = 0.0;
+#pragma omp parallel for reduction(+ : s) schedule(static)
+  for (int64_t i = 0; i < n; ++i) s += a[i] * b[i];
+  return s;
+}
+
+int64_t lvpp_cpu_minres(int64_t n, const int64_t* indptr, const int32_t* indices, const double* vals, const double* pinv,
+                        const double* rhs, double* y, double rtol, int64_t maxit, double* work /* [7 n] */,
+                        double* rnorm_out) {
+  double *r1 = work, *r2 = work + n, *v = work + 2 * n, *z = work + 3 * n, *w = work + 4 * n, *w1 = work + 5 * n,
+         *w2 = work + 6 * n;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    y[i] = 0.0; r1[i] = rhs[i]; r2[i] = rhs[i]; z[i] = pinv[i] * rhs[i]; w[i] = 0.0; w2[i] = 0.0;
+  }
+  double beta1 = dot_omp(n, rhs, z);
+  if (!(beta1 > 0.0)) { if (rnorm_out) *rnorm_out = 0.0; return 0; }
+  beta1 = sqrt(beta1);
+  double oldb = 0.0, beta = beta1, dbar = 0.0, epsln = 0.0, phibar = beta1, cs = -1.0, sn = 0.0;
+  int64_t it = 0;
+  while (it < maxit) {
+    ++it;
+    const double s = 1.0 / beta;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) v[i] = s * z[i];
+    /* z <- A v (reuse z as the product) */
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+      double a = 0.0;
+      for (int64_t p = indptr[i]; p < indptr[i + 1]; ++p) a += vals[p] * v[indices[p]];
+      z[i] = a;
+    }
+    if (it >= 2) {
+      const double c = beta / oldb;
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < n; ++i) z[i] -= c * r1[i];
+    }
+    const double alfa = dot_omp(n, v, z);
+    {
+      const double c = alfa / beta;
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < n; ++i) {
+        const double t = z[i] - c * r2[i];
+        r1[i] = r2[i];
+        r2[i] = t;
+        z[i] = pinv[i] * t;
+      }
+    }
+    oldb = beta;
+    beta = dot_omp(n, r2, z);
+    if (beta < 0.0) break; /* preconditioner not positive */
+    beta = sqrt(beta);
+    /* previous rotation */
+    const double oldeps = epsln;
+    const double delta = cs * dbar + sn * alfa;
+    const double gbar = sn * dbar - cs * alfa;
+    epsln = sn * beta;
+    dbar = -cs * beta;
+    /* next rotation */
+    double gamma = sqrt(gbar * gbar + beta * beta);
+    if (gamma < 1e-300) gamma = 1e-300;
+    cs = gbar / gamma;
+    sn = beta / gamma;
+    const double phi = cs * phibar;
+    phibar = sn * phibar;
+    const double denom = 1.0 / gamma;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+      const double t1 = w2[i];
+      w1[i] = t1;
+      const double t2 = w[i];
+      w2[i] = t2;
+      const double wn = (v[i] - oldeps * t1 - delta * t2) * denom;
+      w[i] = wn;
+      y[i] += phi * wn;
+    }
+    if (phibar <= rtol * beta1 || beta == 0.0) break;
+  }
+  if (rnorm_out) *rnorm_out = phibar;
+  return it;
+}
