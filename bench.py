@@ -177,7 +177,7 @@ def run_reference(args):
 
 def weak_scaling_mesh(n, world, weak="refine", slabs_1gpu=1):
     """Cubes per axis and box of the N-GPU workload: (nxy, nz, lo, hi, slabs).  See the comment in run_b200."""
-    slabs = max(1, slabs_1gpu) if world == 1 else (world if weak == "stack" else 1)
+    slabs = max(1, slabs_1gpu) if world == 1 else (world if weak in ("stack", "stack-open") else 1)
     if world > 1 and weak == "refine":
         nxy = int(round(n * world ** (1.0 / 3.0)))
         # an even number of planes per rank: every rank aggregates from its own first plane, so an odd count leaves a
@@ -225,7 +225,8 @@ def run_b200(args):
         msh = lvpp.mesh.create_rectangle(nxy, nz, rank=rank, nranks=world)
     else:
         nxy, nz, lo, hi, slabs = weak_scaling_mesh(n, world, args.weak, args.slabs)
-        msh = lvpp.mesh.create_box(nxy, nxy, nz, lo=lo, hi=hi, rank=rank, nranks=world)
+        msh = lvpp.mesh.create_box(nxy, nxy, nz, lo=lo, hi=hi, rank=rank, nranks=world,
+                                   clamp_every=n if (slabs > 1 and args.weak != "stack-open") else None)
     opts = {"ksp_rtol": args.ksp_rtol, "ksp_max_it": 200000}
     if args.pc == "mg":
         opts = {"ksp_rtol": args.ksp_rtol, "ksp_type": "gmres", "pc_type": "mg", "ksp_max_it": 400}
@@ -435,7 +436,8 @@ def run_b200(args):
                              ("operator (0.6 GB at N = 1000) and Krylov basis exceed the 126 MB L2; no flush" if dim == 2 and n >= 700 else
                               "inputs fit L2: kernel-level numbers are L2-warm"),
                        "parallelism": f"slab{world}", "weak_scaling": (None if world == 1 else args.weak),
-                       "obstacle": "phi_set of obstacle_pg.py:92-104" + (", one copy per slab (period 2 in z)" if slabs > 1 else "")},
+                       "obstacle": "phi_set of obstacle_pg.py:92-104" + (", one copy per slab (period 2 in z)" if slabs > 1 else "") +
+                                   (", u = 0 on the planes between the slabs" if slabs > 1 and args.weak == "stack" else "")},
             "newton_steps_per_sec": done / secs, "krylov_iterations": kry, "vcycles": s1["vcycles"] - s0["vcycles"],
             "mg_levels": s1["mg_levels"], "wall_s": wall, "setup_s": t_setup,
             "roofline": roofline, "roofline_jv": roof_extra, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
@@ -533,10 +535,11 @@ def main():
                     help="obstacle_pg.py --alpha-scheme (its default: constant)")
     ap.add_argument("--alpha-max", dest="alpha_max", type=float, default=1e5, help="obstacle_pg.py --alpha-max (default 1e5)")
     ap.add_argument("--tol", dest="tol_exit", type=float, default=1e-6, help="obstacle_pg.py --tol (default 1e-6)")
-    ap.add_argument("--weak", default="stack", choices=["refine", "stack"],
+    ap.add_argument("--weak", default="stack", choices=["refine", "stack", "stack-open"],
                     help="N > 1: stack N copies of the n^3 problem along z (default; SURVEY 8d: 215 x 215 x 1720 cubes at 8 GPUs, "
-                         "the mesh width -- and with it the behaviour of the full Newton step -- stays that of one GPU) or "
-                         "refine the mesh of the one-obstacle problem")
+                         "the mesh width -- and with it the behaviour of the full Newton step -- stays that of one GPU), every "
+                         "copy clamped (u = 0) on all six faces like the single box; stack-open: no condition on the "
+                         "planes between the copies; refine: the mesh of the one-obstacle problem refined")
     ap.add_argument("--slabs", type=int, default=1, help="1 GPU only: solve the global problem of an S-GPU run (diagnostic)")
     ap.add_argument("--skip-e2e", dest="no_e2e", action="store_true")
     ap.add_argument("--skip-cpu", dest="no_cpu", action="store_true")

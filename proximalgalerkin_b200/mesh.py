@@ -65,8 +65,9 @@ def _slab(nlayers, rank, nranks):
     return k0, k1, p0, p1
 
 
-def _structured(n, lo, hi, rank, nranks, cube_to_simplices, cell_name):
-    """Common slab machinery.  ``n`` = cube counts per axis (last axis is partitioned)."""
+def _structured(n, lo, hi, rank, nranks, cube_to_simplices, cell_name, clamp_every=None):
+    """Common slab machinery.  ``n`` = cube counts per axis (last axis is partitioned).  ``clamp_every``: vertex planes
+    of the last axis whose index is a multiple of it count as boundary as well (a stack of clamped membranes)."""
     dim = len(n)
     nv = [m + 1 for m in n]
     plane = int(np.prod(nv[:-1]))  # vertices per layer of the last axis
@@ -112,6 +113,8 @@ def _structured(n, lo, hi, rank, nranks, cube_to_simplices, cell_name):
         onb |= (c == 0) | (c == n[d])
     kk = gv // plane
     onb |= (kk == 0) | (kk == n[-1])
+    if clamp_every:
+        onb |= (kk % int(clamp_every)) == 0
     # halo
     halo = Halo()
     ar = np.arange(plane, dtype=np.int32)
@@ -171,9 +174,11 @@ def create_rectangle(nx, ny, lo=(-1.0, -1.0), hi=(1.0, 1.0), rank=0, nranks=1, d
     return _structured((nx, ny), lo, hi, rank, nranks, split, "triangle")
 
 
-def create_box(nx, ny, nz, lo=(-1.0, -1.0, -1.0), hi=(1.0, 1.0, 1.0), rank=0, nranks=1):
+def create_box(nx, ny, nz, lo=(-1.0, -1.0, -1.0), hi=(1.0, 1.0, 1.0), rank=0, nranks=1, clamp_every=None):
     """[lo, hi] box, nx x ny x nz cubes, each split into six Kuhn tetrahedra sharing the main
-    diagonal; partitioned into slabs along z."""
+    diagonal; partitioned into slabs along z.  ``clamp_every = m`` adds the vertex planes z-index = 0, m, 2m, ... to
+    ``boundary_vertices`` (bench.py's weak-scaling workload: copies of one box stacked along z, each clamped on all
+    six faces)."""
 
     def split(base, strides, lo_off, hi_off):
         # corner (dx, dy, dz) of the cube -> local vertex number
@@ -190,7 +195,7 @@ def create_box(nx, ny, nz, lo=(-1.0, -1.0, -1.0), hi=(1.0, 1.0, 1.0), rank=0, nr
             tets.append(np.stack(verts, 1))
         return np.stack(tets, axis=1).reshape(-1, 4)
 
-    return _structured((nx, ny, nz), lo, hi, rank, nranks, split, "tetrahedron")
+    return _structured((nx, ny, nz), lo, hi, rank, nranks, split, "tetrahedron", clamp_every)
 
 
 def from_arrays(coords, cells, boundary_vertices=None):
