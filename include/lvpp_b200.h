@@ -117,6 +117,11 @@ typedef struct lvpp_newton_opts {
   int32_t snes_linesearch; /* LVPP_LINESEARCH_*: "none"/"basic" (obstacle_pg.py:136) or PETSc's default "bt"
                               (examples/04_multiphase/multiphase_dolfinx.py:128-143 sets none); lvpp_form_* only */
   int32_t ksp_restart;     /* GMRES restart length of the lvpp_form_* solver (0 = 200) */
+  double psi_increase_max; /* 0 = off (the reference: full Newton step, obstacle_pg.py:136).  > 0: no component of the
+                              latent variable grows by more than this in one Newton step of the obstacle engine -- a
+                              safeguard that is NOT in the reference, for meshes on which its full step overshoots
+                              (exp(psi) next to the contact boundary).  Steps whose psi increments stay
+                              below the bound are the reference's steps, bit for bit. */
 } lvpp_newton_opts;
 
 #define LVPP_LINESEARCH_NONE 0

@@ -80,11 +80,12 @@ class NewtonOpts(C.Structure):
         ("pc_degree", C.c_int32),
         ("snes_linesearch", C.c_int32),
         ("ksp_restart", C.c_int32),
+        ("psi_increase_max", C.c_double),
     ]
 
     @classmethod
     def defaults(cls):
-        return cls(1e-8, 1e-50, 1e-8, 1e4, 50, 1e-12, 1e-50, 100000, PC_JACOBI, 0, LINESEARCH_NONE, 0)
+        return cls(1e-8, 1e-50, 1e-8, 1e4, 50, 1e-12, 1e-50, 100000, PC_JACOBI, 0, LINESEARCH_NONE, 0, 0.0)
 
 
 class IntegralDesc(C.Structure):

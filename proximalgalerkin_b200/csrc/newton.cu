@@ -6,16 +6,18 @@
 
 #include "lvpp_internal.cuh"
 
-// x <- x - y on the owned rows; partial ||y||^2 and ||x_new||^2  (the fused Newton update + norms)
+// x <- x - y on the owned rows; partial ||y||^2 and ||x_new||^2  (the fused Newton update + norms).
+// cap > 0 (lvpp_newton_opts.psi_increase_max, not in the reference): psi grows by at most cap per step.
 __global__ void __launch_bounds__(256)
 k_newton_update(int64_t Vown, double2* __restrict__ x, const double2* __restrict__ y, int nparts,
-                double* __restrict__ partials) {
+                double* __restrict__ partials, double cap) {
   __shared__ double s_red[32];
   double py = 0.0, px = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vown;
        i += (int64_t)gridDim.x * blockDim.x) {
     double2 a = x[i];
-    const double2 b = y[i];
+    double2 b = y[i];
+    if (cap > 0.0 && b.y < -cap) b.y = -cap;
     a.x -= b.x;
     a.y -= b.y;
     x[i] = a;
@@ -77,7 +79,7 @@ extern "C" int lvpp_newton_step(lvpp_handle h, double* d_x, const lvpp_newton_op
   if (ksp_reason) *ksp_reason = kreason;
   CK(cudaEventRecord(h->ev0, h->stream));
   LAUNCH(h, k_newton_update, h->npartials, 256, 0, h->Vown, (double2*)d_x, (const double2*)h->y, h->npartials,
-         h->partials);
+         h->partials, opts->psi_increase_max);
   CK(cudaGetLastError());
   CKR(lvpp_reduce_partials(h, 2, h->scal->red + 1));
   CKR(lvpp_eval_residual(h, d_x, h->F, true));  // writes red[0]

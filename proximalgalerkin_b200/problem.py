@@ -359,6 +359,10 @@ def newton_options(options, generic=False):
         raise NotImplementedError(f"snes_linesearch_type {ls!r}")
     # snes_linesearch_maxlambda (PETSc >= 3.23; fracture_dolfinx.py:135) / snes_linesearch_maxstep (older name)
     o.linesearch_maxstep = float(opts.get("snes_linesearch_maxlambda", opts.get("snes_linesearch_maxstep", 1e8)))
+    # not a PETSc option: bound on the growth of psi per Newton step of the obstacle engine (lvpp_newton_opts.psi_increase_max;
+    # off by default = the reference's full step)
+    if opts.get("lvpp_psi_increase_max") is not None:
+        o.psi_increase_max = float(opts["lvpp_psi_increase_max"])
     if opts.get("ksp_gmres_restart") is not None:
         o.ksp_restart = int(opts["ksp_gmres_restart"])
     st = opts.get("snes_type", "newtonls")

@@ -130,3 +130,22 @@ def test_mid_solve_linear_solve_matches_host_lu_on_both_row_blocks(lib, kind, n)
     scale_u, scale_p = np.abs(J[0::2]).sum(axis=1).max(), np.abs(J[1::2]).sum(axis=1).max()  # row scales of the two blocks
     assert np.linalg.norm(r[0::2]) <= 1e-9 * scale_u * np.linalg.norm(y) / np.sqrt(y.size)
     assert np.linalg.norm(r[1::2]) <= 1e-9 * scale_p * np.linalg.norm(y) / np.sqrt(y.size)
+
+
+def test_psi_increase_bound_is_inactive_when_large_and_converges_when_small(lib):
+    """lvpp_psi_increase_max (not in the reference): a bound no step reaches leaves the whole LVPP solve
+    bit-identical to the reference's full Newton step; a small bound changes the Newton path, not the solution."""
+    import proximalgalerkin_b200 as lvpp
+
+    def run(extra):
+        msh = lvpp.mesh.create_box(10, 10, 10)
+        sol, total, h = lvpp.obstacle_pg.solve_problem(msh, 1, 500, "double_exponential", 1e2, 1e-4, petsc_options=dict(MG, **extra))
+        return sol.x.array.copy(), h
+
+    x0, h0 = run({})
+    x1, h1 = run({"lvpp_psi_increase_max": 1e3})
+    assert h1["newton_steps"] == h0["newton_steps"] and np.array_equal(x0, x1)
+    x2, h2 = run({"lvpp_psi_increase_max": 0.5})
+    assert sum(h2["newton_steps"]) >= sum(h0["newton_steps"])
+    u0, u2 = x0[0::2], x2[0::2]
+    assert np.linalg.norm(u2 - u0) <= 2e-4 * np.linalg.norm(u0)  # both stop on an increment of 1e-4

@@ -19,6 +19,8 @@ def main():
     ap.add_argument("--size", type=int, default=215)
     ap.add_argument("--nz", type=int, default=None, help="cubes along z over all ranks (default: --size)")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--psi-cap", dest="psi_cap", type=float, default=None,
+                    help="lvpp_psi_increase_max: bound on the growth of psi per Newton step (not in the reference)")
     ap.add_argument("--tol", type=float, default=1e-4, help="tol_exit of the outer loop (CI: 1e-4; script default 1e-6)")
     ap.add_argument("--alpha-max", dest="alpha_max", type=float, default=1e2)
     ap.add_argument("--pc", default="mg")
@@ -48,6 +50,8 @@ def main():
     msh = lvpp.mesh.create_box(n, n, nz, rank=rank, nranks=world)
     opts = {"ksp_rtol": 1e-12, "ksp_type": "gmres", "pc_type": "mg"} if args.pc == "mg" else {"ksp_rtol": 1e-12}
     opts["snes_linesearch_type"] = args.linesearch
+    if args.psi_cap is not None:
+        opts["lvpp_psi_increase_max"] = args.psi_cap
     if args.snes_rtol is not None:
         opts["snes_rtol"] = args.snes_rtol
     if args.alpha_scheme == "adaptive":  # a failed solve is reported as a reason, not raised
@@ -89,7 +93,7 @@ def main():
     if rank == 0:
         print(json.dumps({
             "workload": f"3-D P1 obstacle LVPP, {n}x{n}x{nz} cubes x 6 tets, full solve ({args.alpha_scheme} alpha, alpha_max 1e2, tol 1e-4)",
-            "tag": args.tag, "linesearch": args.linesearch, "snes_rtol": args.snes_rtol, "failure": failure,
+            "tag": args.tag, "psi_cap": args.psi_cap, "linesearch": args.linesearch, "snes_rtol": args.snes_rtol, "failure": failure,
             "n_gpus": world, "rows": s["num_rows"], "setup_s": t_setup, "solve_s": t_solve,
             "newton_steps": st.total_newton, "krylov_iterations": st.total_krylov, "outer_steps": len(st.history["newton_steps"]),
             "dofs_per_sec": s["num_rows"] * st.total_newton / t_solve, "history": st.history,
