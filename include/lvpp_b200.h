@@ -122,6 +122,10 @@ typedef struct lvpp_newton_opts {
                               safeguard that is NOT in the reference, for meshes on which its full step overshoots
                               (exp(psi) next to the contact boundary).  Steps whose psi increments stay
                               below the bound are the reference's steps, bit for bit. */
+  double psi_free_below;   /* with psi_increase_max > 0: psi may rise freely up to this value and by at most
+                              psi_increase_max per step beyond it, psi_new <= max(psi_old, psi_free_below) +
+                              psi_increase_max (a node that leaves the contact set comes up from -100 in one step and
+                              still cannot overshoot).  -1e300 = none: the bound applies to every increment. */
 } lvpp_newton_opts;
 
 #define LVPP_LINESEARCH_NONE 0

@@ -81,11 +81,12 @@ class NewtonOpts(C.Structure):
         ("snes_linesearch", C.c_int32),
         ("ksp_restart", C.c_int32),
         ("psi_increase_max", C.c_double),
+        ("psi_free_below", C.c_double),
     ]
 
     @classmethod
     def defaults(cls):
-        return cls(1e-8, 1e-50, 1e-8, 1e4, 50, 1e-12, 1e-50, 100000, PC_JACOBI, 0, LINESEARCH_NONE, 0, 0.0)
+        return cls(1e-8, 1e-50, 1e-8, 1e4, 50, 1e-12, 1e-50, 100000, PC_JACOBI, 0, LINESEARCH_NONE, 0, 0.0, -1e300)
 
 
 class IntegralDesc(C.Structure):

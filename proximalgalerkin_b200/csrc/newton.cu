@@ -7,17 +7,21 @@
 #include "lvpp_internal.cuh"
 
 // x <- x - y on the owned rows; partial ||y||^2 and ||x_new||^2  (the fused Newton update + norms).
-// cap > 0 (lvpp_newton_opts.psi_increase_max, not in the reference): psi grows by at most cap per step.
+// cap > 0 (lvpp_newton_opts.psi_increase_max / psi_free_below, not in the reference):
+// psi_new <= max(psi_old, free_below) + cap.
 __global__ void __launch_bounds__(256)
 k_newton_update(int64_t Vown, double2* __restrict__ x, const double2* __restrict__ y, int nparts,
-                double* __restrict__ partials, double cap) {
+                double* __restrict__ partials, double cap, double free_below) {
   __shared__ double s_red[32];
   double py = 0.0, px = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Vown;
        i += (int64_t)gridDim.x * blockDim.x) {
     double2 a = x[i];
     double2 b = y[i];
-    if (cap > 0.0 && b.y < -cap) b.y = -cap;
+    if (cap > 0.0) {
+      const double top = fmax(a.y, free_below) + cap;  // the highest psi this step may reach
+      if (a.y - b.y > top) b.y = a.y - top;
+    }
     a.x -= b.x;
     a.y -= b.y;
     x[i] = a;
@@ -79,7 +83,7 @@ extern "C" int lvpp_newton_step(lvpp_handle h, double* d_x, const lvpp_newton_op
   if (ksp_reason) *ksp_reason = kreason;
   CK(cudaEventRecord(h->ev0, h->stream));
   LAUNCH(h, k_newton_update, h->npartials, 256, 0, h->Vown, (double2*)d_x, (const double2*)h->y, h->npartials,
-         h->partials, opts->psi_increase_max);
+         h->partials, opts->psi_increase_max, opts->psi_free_below);
   CK(cudaGetLastError());
   CKR(lvpp_reduce_partials(h, 2, h->scal->red + 1));
   CKR(lvpp_eval_residual(h, d_x, h->F, true));  // writes red[0]

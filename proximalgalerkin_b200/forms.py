@@ -230,3 +230,71 @@ class FormNonlinearProblem:
 
             raise NotConvergedError(f"SNES did not converge: reason {reason} after {its} iterations", reason, its)
         return self.x
+
+
+
+# ---------------------------------------------------------------------------------------------
+# blocked problems: NonlinearProblem(F, [u, psi], bcs=..., J=..., entity_maps=..., kind="mpi")
+# (examples/02_signorini/signorini_dolfinx.py:283-291)
+class _Vec:
+    def __init__(self, n):
+        self.array = np.zeros(n)
+
+
+class BlockFunction:
+    """One unknown of a blocked problem (``fem.Function(V)`` / ``fem.Function(W)``, signorini_dolfinx.py:227-228):
+    ``.x.array`` is the host vector the driver reads and mutates."""
+
+    def __init__(self, n, name="f"):
+        self.x = _Vec(n)
+        self.name = name
+
+
+class BlockedForm:
+    """What ``ufl.extract_blocks(residual)`` (signorini_dolfinx.py:252) is to the reference: the residual blocks of a
+    :class:`FormProblem` whose unknown is the concatenation of ``unknowns``.  ``sync`` pushes the form's mutable inputs
+    (``alpha.value``, ``psi_k.x.array``, Dirichlet values) to the device the way a dolfinx assembly reads them at
+    call time."""
+
+    def __init__(self, dev: FormProblem, unknowns, sync=None):
+        self.dev = dev
+        self.unknowns = list(unknowns)
+        self.sizes = [f.x.array.size for f in self.unknowns]
+        if sum(self.sizes) != dev.n:
+            raise ValueError("block sizes do not add up to the number of dofs of the form")
+        self.sync = sync or (lambda: None)
+
+
+class BlockedNonlinearProblem:
+    """``NonlinearProblem(F, [u, psi], ...)``: gathers the blocks into the mixed vector, runs the Newton loop on the
+    device, scatters the iterate back into the blocks (whatever the reason, like dolfinx)."""
+
+    def __init__(self, F: BlockedForm, u, petsc_options=None):
+        if [id(f) for f in u] != [id(f) for f in F.unknowns]:
+            raise ValueError("u must be the list of unknowns the blocked form was written in")
+        self.F = F
+        self._x = np.zeros(F.dev.n)
+        self._inner = FormNonlinearProblem(F.dev, self._x, petsc_options)
+        self.solver = self._inner.solver
+        self.u = list(u)
+
+    def _gather(self):
+        off = 0
+        for f, n in zip(self.F.unknowns, self.F.sizes):
+            self._x[off:off + n] = f.x.array
+            off += n
+
+    def _scatter(self):
+        off = 0
+        for f, n in zip(self.F.unknowns, self.F.sizes):
+            f.x.array[:] = self._x[off:off + n]
+            off += n
+
+    def solve(self):
+        self.F.sync()
+        self._gather()
+        try:
+            self._inner.solve()
+        finally:
+            self._scatter()
+        return self.u

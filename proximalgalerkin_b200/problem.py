@@ -363,6 +363,8 @@ def newton_options(options, generic=False):
     # off by default = the reference's full step)
     if opts.get("lvpp_psi_increase_max") is not None:
         o.psi_increase_max = float(opts["lvpp_psi_increase_max"])
+    if opts.get("lvpp_psi_free_below") is not None:
+        o.psi_free_below = float(opts["lvpp_psi_free_below"])
     if opts.get("ksp_gmres_restart") is not None:
         o.ksp_restart = int(opts["ksp_gmres_restart"])
     st = opts.get("snes_type", "newtonls")
@@ -571,7 +573,19 @@ class NonlinearProblem:
     def __init__(self, F, u, bcs=None, J=None, petsc_options=None, petsc_options_prefix="", entity_maps=None,
                  kind=None, jit_options=None, form_compiler_options=None):
         if isinstance(u, (list, tuple)):
-            raise NotImplementedError("blocked problems (list of unknowns) are not on this path")
+            # blocked problem (signorini_dolfinx.py:283-291: F = extract_blocks(residual), u = [u, psi], entity_maps,
+            # kind="mpi"): the mixed-form engine, forms.BlockedNonlinearProblem
+            from .forms import BlockedForm, BlockedNonlinearProblem
+
+            if not isinstance(F, BlockedForm):
+                raise TypeError("a list of unknowns needs a blocked form (forms.BlockedForm, e.g. signorini.setup()['F'])")
+            self._blocked = BlockedNonlinearProblem(F, u, petsc_options)
+            self._options = dict(petsc_options or {})
+            self.solver = self._blocked.solver
+            self.u = list(u)
+            self.prefix = petsc_options_prefix
+            return
+        self._blocked = None
         self._problem = SNESProblem(F, u, J=J, bcs=bcs)
         self._options = dict(petsc_options or {})
         self._snes = SNESSolver(self._problem, self._options)
@@ -581,9 +595,11 @@ class NonlinearProblem:
 
     @property
     def device_problem(self):
-        return self._problem.device_problem
+        return self._blocked.F.dev if self._blocked is not None else self._problem.device_problem
 
     def solve(self):
+        if self._blocked is not None:
+            return self._blocked.solve()
         reason, its = self._snes.solve(copy_on_failure=True)  # dolfinx leaves the last iterate in u whatever the reason
         if reason == SNES_DIVERGED_LINEAR_SOLVE and _flag(self._options, "ksp_error_if_not_converged"):
             raise NotConvergedError("KSP did not converge (ksp_error_if_not_converged)", reason, its)

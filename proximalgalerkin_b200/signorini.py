@@ -10,7 +10,8 @@ step (:272-281,331-332).  Mixed dof numbering: u at vertex n -> 3 n + c; psi at 
 import numpy as np
 
 from . import _capi, fem, mesh as _mesh, quadrature
-from .forms import FormNonlinearProblem, FormProblem, Integral
+from .forms import BlockedForm, BlockFunction, FormProblem, Integral
+from .problem import NonlinearProblem
 
 
 def exterior_facets(cells):
@@ -58,9 +59,23 @@ def setup(msh, E=2.0e4, nu=0.3, gap=0.0, disp=-0.25, quadrature_degree=4, alpha_
         "ksp_error_if_not_converged": True, "snes_error_if_not_converged": True,
     }
     opts.update(petsc_options or {})
-    sol = np.zeros(n)
-    return {"mesh": msh, "dev": dev, "sol": sol, "problem": FormNonlinearProblem(dev, sol, opts), "num_u": 3 * N,
-            "bc_vertices": bc_vertices, "sub_vertices": sub_vertices}
+    # unknowns and mutable inputs of the blocked form (signorini_dolfinx.py:227-232,240-252)
+    u, psi, psi_k = BlockFunction(3 * N, "u"), BlockFunction(sub_vertices.size, "psi"), BlockFunction(sub_vertices.size, "psi_k")
+    alpha = fem.Constant(msh, alpha_0)
+    aux = np.zeros(n)
+
+    def sync():  # what a dolfinx assembly reads at call time: alpha.value, psi_k.x.array
+        dev.set_param(0, alpha.value)
+        aux[3 * N:] = psi_k.x.array
+        dev.set_aux(0, aux)
+
+    F = BlockedForm(dev, [u, psi], sync)
+    # signorini_dolfinx.py:283-291: NonlinearProblem(F, [u, psi], bcs=bcs, J=J, entity_maps=..., kind="mpi", ...)
+    problem = NonlinearProblem(F, [u, psi], bcs=None, J=None, petsc_options=opts, petsc_options_prefix="signorini_",
+                               entity_maps=None, kind="mpi")
+    # "sol": the mixed host vector [u; psi] behind the two blocks (gathered before, scattered after every solve)
+    return {"mesh": msh, "dev": dev, "F": F, "u": u, "psi": psi, "psi_k": psi_k, "alpha": alpha, "problem": problem,
+            "sol": problem._blocked._x, "num_u": 3 * N, "bc_vertices": bc_vertices, "sub_vertices": sub_vertices}
 
 
 def solve_contact_problem(mesh, facet_tag=None, boundary_conditions=None, degree=1, E=2.0e4, nu=0.3, gap=0.0,
@@ -76,9 +91,8 @@ def solve_contact_problem(mesh, facet_tag=None, boundary_conditions=None, degree
         raise NotImplementedError("degree 1")
     bcnd = boundary_conditions or {}
     s = setup(mesh, E, nu, gap, disp, quadrature_degree, alpha_0, bcnd.get("contact"), bcnd.get("displacement"), petsc_options)
-    dev, sol, problem, nu_dofs = s["dev"], s["sol"], s["problem"], s["num_u"]
-    u_prev = np.zeros(nu_dofs)
-    psi_k = np.zeros_like(sol)
+    u, psi, psi_k, alpha_c_, problem = s["u"], s["psi"], s["psi_k"], s["alpha"], s["problem"]
+    u_prev = np.zeros_like(u.x.array)
     iterations = []
     it = 0
     for it in range(1, max_iterations + 1):
@@ -87,19 +101,18 @@ def solve_contact_problem(mesh, facet_tag=None, boundary_conditions=None, degree
             alpha = alpha_0 + alpha_c * it
         elif alpha_scheme == "doubling":
             alpha = alpha_0 * 2**it
-        dev.set_param(0, alpha)
-        dev.set_aux(0, psi_k)
+        alpha_c_.value = alpha
         solver_tol = 10 * newton_tol if it < 2 else newton_tol  # :331-332
         problem.solver.setTolerances(atol=solver_tol, rtol=solver_tol)
         problem.solve()
         iterations.append(problem.solver.getIterationNumber())
-        normed_diff = float(np.linalg.norm(sol[:nu_dofs] - u_prev))  # :337-339 (host copy of the device result)
+        normed_diff = float(np.linalg.norm(u.x.array - u_prev))  # :337-339 (host copy of the device result)
         if verbose:
             print(f"it={it}/{max_iterations} alpha={alpha} newton={iterations[-1]} increment {normed_diff:.2e}")
         if normed_diff <= tol:
             break
-        u_prev[:] = sol[:nu_dofs]
-        psi_k[nu_dofs:] = sol[nu_dofs:]  # :344
+        u_prev[:] = u.x.array
+        psi_k.x.array[:] = psi.x.array  # :344
         if problem.solver.getConvergedReason() <= 0:
             break
     solve_contact_problem.last = s

@@ -138,6 +138,13 @@ def test_signorini_lvpp_matches_oracle(lib, disp):
     msh = lvpp.mesh.create_box(n, n, n, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0))
     it, iterations = lvpp.signorini.solve_contact_problem(msh, disp=disp, alpha_0=0.005, petsc_options={"ksp_gmres_restart": 400})
     assert it == ho["it"] and iterations == ho["iterations"]
-    sol = lvpp.signorini.solve_contact_problem.last["sol"]
+    last = lvpp.signorini.solve_contact_problem.last
+    sol = last["sol"]
     nu = 3 * orc.N
     assert np.linalg.norm(sol[:nu] - xo[:nu]) <= 1e-9 * np.linalg.norm(xo[:nu])
+    # the blocked call shape of signorini_dolfinx.py:283-291: NonlinearProblem(F, [u, psi], ...) keeps the two blocks in
+    # the caller's functions
+    assert isinstance(last["problem"], lvpp.NonlinearProblem) and last["problem"].u == [last["u"], last["psi"]]
+    assert np.array_equal(last["u"].x.array, sol[:nu]) and np.array_equal(last["psi"].x.array, sol[nu:])
+    with pytest.raises(TypeError):
+        lvpp.NonlinearProblem(object(), [last["u"], last["psi"]])

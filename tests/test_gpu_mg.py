@@ -149,3 +149,18 @@ def test_psi_increase_bound_is_inactive_when_large_and_converges_when_small(lib)
     assert sum(h2["newton_steps"]) >= sum(h0["newton_steps"])
     u0, u2 = x0[0::2], x2[0::2]
     assert np.linalg.norm(u2 - u0) <= 2e-4 * np.linalg.norm(u0)  # both stop on an increment of 1e-4
+
+
+def test_psi_bound_with_free_rise_converges(lib):
+    """lvpp_psi_free_below: psi may rise freely up to the given value and by psi_increase_max per step beyond it."""
+    import proximalgalerkin_b200 as lvpp
+
+    def run(extra):
+        msh = lvpp.mesh.create_box(10, 10, 10)
+        sol, total, h = lvpp.obstacle_pg.solve_problem(msh, 1, 500, "double_exponential", 1e2, 1e-4, petsc_options=dict(MG, **extra))
+        return sol.x.array.copy(), h
+
+    x0, h0 = run({})
+    x1, h1 = run({"lvpp_psi_increase_max": 1.0, "lvpp_psi_free_below": 0.0})
+    assert np.linalg.norm(x1[0::2] - x0[0::2]) <= 2e-4 * np.linalg.norm(x0[0::2])
+    assert sum(h1["newton_steps"]) <= sum(h0["newton_steps"]) + 6

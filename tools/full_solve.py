@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--size", type=int, default=215)
     ap.add_argument("--nz", type=int, default=None, help="cubes along z over all ranks (default: --size)")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--psi-free", dest="psi_free", type=float, default=None, help="lvpp_psi_free_below")
     ap.add_argument("--psi-cap", dest="psi_cap", type=float, default=None,
                     help="lvpp_psi_increase_max: bound on the growth of psi per Newton step (not in the reference)")
     ap.add_argument("--tol", type=float, default=1e-4, help="tol_exit of the outer loop (CI: 1e-4; script default 1e-6)")
@@ -52,6 +53,8 @@ def main():
     opts["snes_linesearch_type"] = args.linesearch
     if args.psi_cap is not None:
         opts["lvpp_psi_increase_max"] = args.psi_cap
+    if args.psi_free is not None:
+        opts["lvpp_psi_free_below"] = args.psi_free
     if args.snes_rtol is not None:
         opts["snes_rtol"] = args.snes_rtol
     if args.alpha_scheme == "adaptive":  # a failed solve is reported as a reason, not raised
