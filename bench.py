@@ -230,6 +230,11 @@ def run_b200(args):
     opts = {"ksp_rtol": args.ksp_rtol, "ksp_max_it": 200000}
     if args.pc == "mg":
         opts = {"ksp_rtol": args.ksp_rtol, "ksp_type": "gmres", "pc_type": "mg", "ksp_max_it": 400}
+    if args.psi_cap is not None:  # the safeguard that is not in the reference; off for the headline line
+        opts["lvpp_psi_increase_max"] = args.psi_cap
+        opts["ksp_max_it"] = 4000
+        if args.psi_free is not None:
+            opts["lvpp_psi_free_below"] = args.psi_free
     st = lvpp.obstacle_pg.LvppStepper(msh, 1, args.alpha_scheme, args.alpha_max, args.tol_exit, max_outer=100, petsc_options=opts,
                                       obstacle_period=2.0 if slabs > 1 else None, obstacle_origin=-float(slabs))
     dev = st.dev
@@ -429,7 +434,8 @@ def run_b200(args):
                                    f"{rows_global} rows, {stats0['nnz']} nnz/GPU (CSR-equivalent)",
                        "n": n, "rows": rows_global, "primal_dofs": rows_global // 2,  # the reference's CSV column "dofs" (obstacle_pg.py:237,255)
                        "alpha_scheme": args.alpha_scheme, "alpha_max": args.alpha_max, "tol_exit": args.tol_exit, "max_outer": 100,
-                       "schedule_note": SCHEDULE_NOTE, "snes_linesearch_type": "none", "snes_rtol": 1e-6, "ksp": ("MINRES + block-Jacobi/Schur-diag" if args.pc == "jacobi" else
+                       "schedule_note": SCHEDULE_NOTE, "snes_linesearch_type": "none",
+                       "psi_increase_max": args.psi_cap, "psi_free_below": args.psi_free, "snes_rtol": 1e-6, "ksp": ("MINRES + block-Jacobi/Schur-diag" if args.pc == "jacobi" else
                                "GMRES(50) + monolithic aggregation multigrid V(2,3) (node-block Jacobi sweeps with Chebyshev-root "
                                "dampings, ratio 6; cycle operator from packed bf16 pair records with fp64 accumulation, fp64 Krylov operator)"), "ksp_rtol": args.ksp_rtol,
                        "l2": "operator (>=4 GB) and vectors exceed the 126 MB L2; no flush needed" if (dim == 3 and n >= 100) else
@@ -535,6 +541,9 @@ def main():
                     help="obstacle_pg.py --alpha-scheme (its default: constant)")
     ap.add_argument("--alpha-max", dest="alpha_max", type=float, default=1e5, help="obstacle_pg.py --alpha-max (default 1e5)")
     ap.add_argument("--tol", dest="tol_exit", type=float, default=1e-6, help="obstacle_pg.py --tol (default 1e-6)")
+    ap.add_argument("--psi-cap", dest="psi_cap", type=float, default=None,
+                    help="lvpp_psi_increase_max (NOT in the reference; off by default): bound on the growth of psi per Newton step")
+    ap.add_argument("--psi-free", dest="psi_free", type=float, default=None, help="lvpp_psi_free_below (with --psi-cap)")
     ap.add_argument("--weak", default="stack", choices=["refine", "stack", "stack-open"],
                     help="N > 1: stack N copies of the n^3 problem along z (default; SURVEY 8d: 215 x 215 x 1720 cubes at 8 GPUs, "
                          "the mesh width -- and with it the behaviour of the full Newton step -- stays that of one GPU), every "

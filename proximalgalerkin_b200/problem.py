@@ -452,6 +452,7 @@ class SNESProblem:
         with scale -1 and x0 = x, reverse scatter, set_bc -- problem.py:54-67 -- all on the device)."""
         dev = self.device_problem
         dev.sync_coefficients()
+        self._mirror(x)
         return dev.assemble_residual(x, F)
 
     def J(self, snes, x, J, P=None):
@@ -459,7 +460,17 @@ class SNESProblem:
         problem.py:69-77)."""
         dev = self.device_problem
         dev.sync_coefficients()
+        self._mirror(x)
         dev.assemble_jacobian(x)
+
+    #: the reference's callbacks copy the iterate into ``u`` at every call (problem.py:57,72: ``x.copy(self.u.x.petsc_vec)``).
+    #: Here the iterate lives in HBM and ``u.x.array`` is a host vector, so that copy is a device-to-host transfer of the
+    #: whole vector per callback; it is done only when this flag is set (a caller that reads ``u`` inside a monitor).
+    mirror_iterate = False
+
+    def _mirror(self, x):
+        if self.mirror_iterate:
+            self.u.x.array[:] = x.numpy()
 
 
 class NotConvergedError(RuntimeError):
