@@ -5,7 +5,7 @@ own API surface (src/lvpp/__init__.py:1-9 exports ``SNESProblem`` and ``SNESSolv
 use the ``NonlinearProblem(...).solve()`` call shape).  Host code is Python; all arithmetic runs in
 hand-written sm_100a CUDA kernels reached through the C ABI of ``include/lvpp_b200.h``.
 """
-from . import fem, forms, gradient_constraints, mesh, multiphase, obstacle_pg, quadrature, signorini
+from . import fem, forms, gradient_constraints, io, mesh, multiphase, obstacle_pg, quadrature, signorini
 from .problem import (
     DeviceMatrix,
     DeviceProblem,
@@ -32,6 +32,7 @@ __all__ = [
     "newton_options",
     "fem",
     "mesh",
+    "io",
     "quadrature",
     "obstacle_pg",
     "forms",

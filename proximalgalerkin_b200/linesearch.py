@@ -162,7 +162,9 @@ def linesearch_l2(be, x, y, w, G, fnorm, lam0=1.0, maxstep=1e8, steptol=1e-12, m
         curv = (slope_hi - slope_lo) / width
         if curv == 0.0:
             break
-        cand = hi - slope_hi / abs(curv)                          # secant (Newton) step on phi', always downhill
+        # secant (Newton) step on phi'; PETSc's SNESLineSearchApply_L2 takes lambda - del/del2 for del2 > 0 and
+        # lambda + del/del2 for del2 < 0 ("always go downhill"), i.e. the division by |del2| below
+        cand = hi - slope_hi / abs(curv)
         if cand < steptol:
             cand = 0.5 * (hi + lo)
         if not math.isfinite(cand) or cand > maxstep:

@@ -68,7 +68,8 @@ def setup(msh, polynomial_order=1, quadrature_degree=6, obstacle="phi_set", f_va
 
 
 def solve_problem(msh, polynomial_order=1, maximum_number_of_outer_loop_iterations=100, alpha_scheme="constant",
-                  alpha_max=1e5, tol_exit=1e-6, obstacle="phi_set", petsc_options=None, verbose=False, adaptive=None):
+                  alpha_max=1e5, tol_exit=1e-6, obstacle="phi_set", petsc_options=None, verbose=False, adaptive=None,
+                  output_dir=None):
     """Returns (sol, total Newton steps, history dict) -- the reference returns (sol, sum(Newton_steps))
     and writes the history to CSV (obstacle_pg.py:245-264).
 
@@ -136,6 +137,17 @@ def solve_problem(msh, polynomial_order=1, maximum_number_of_outer_loop_iteratio
             ctl.accepted(n)
         sol_k.x.array[:] = sol.x.array[:]
         k += 1
+    if output_dir is not None and msh.rank == 0:
+        # obstacle_pg.py:229-259: the solution for ParaView (VTX there, .vtu here; P1 fields) and the history table as CSV
+        from pathlib import Path
+
+        from . import io
+
+        out = Path(output_dir)
+        out.mkdir(parents=True, exist_ok=True)
+        if polynomial_order == 1 and msh.nranks == 1:
+            io.write_solution(out / "solution.vtu", s["V"], sol.x.array)
+        io.write_history_csv(out / f"pg_{alpha_scheme}_p{polynomial_order}.csv", hist, dofs=s["V"].num_rows // 2)
     return sol, sum(hist["newton_steps"]), hist
 
 

@@ -139,3 +139,22 @@ def test_bench_weak_scaling_mesh():
         assert abs(per_gpu / 215**3 - 1.0) < 0.015
     assert bench.weak_scaling_mesh(215, 8, "stack") == (215, 1720, (-1.0, -1.0, -8.0), (1.0, 1.0, 8.0), 8)
     assert bench.weak_scaling_mesh(215, 1, "refine", 2) == (215, 430, (-1.0, -1.0, -2.0), (1.0, 1.0, 2.0), 2)
+
+
+@pytest.mark.parametrize("cell,tdim", [("triangle", 2), ("tetrahedron", 3)])
+@pytest.mark.parametrize("deg", [1, 2, 4, 6, 10])
+def test_product_quadrature_integrates_monomials_exactly(cell, tdim, deg):
+    """The product's quadrature tables checked on their own (not against the oracle's copy of the same numbers): every
+    monomial of total degree <= deg is integrated exactly over the reference simplex,
+    int x^a y^b z^c = a! b! c! / (a + b + c + d)!, weights positive, points inside."""
+    from itertools import product as iproduct
+    from math import factorial
+
+    p, w = lvpp.quadrature.make_quadrature(cell, deg)
+    assert p.shape[1] == tdim and np.all(w > 0) and np.all(p > -1e-14) and np.all(p.sum(axis=1) < 1 + 1e-14)
+    for e in iproduct(range(deg + 1), repeat=tdim):
+        if sum(e) > deg:
+            continue
+        exact = np.prod([factorial(k) for k in e]) / factorial(sum(e) + tdim)
+        val = float(np.sum(w * np.prod(p ** np.array(e), axis=1)))
+        assert abs(val - exact) <= 2e-15 * max(1.0, 1.0 / exact) * exact + 1e-17, (e, val, exact)
