@@ -524,8 +524,8 @@ def run_forms(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20, help="timed Newton steps (default 20: with --warmup 5, steps 6-25 of a whole solve)")
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--size", dest="n", type=int, default=215, help="cubes per axis per GPU")
     ap.add_argument("--cpu-size", dest="n_cpu", type=int, default=20,
                     help="cubes per axis of the CPU sample (20: 18 522 rows, ~10 s for 6 Newton steps with sparse LU)")

@@ -77,6 +77,11 @@ struct lvpp_form_problem {
   int gm_restart = 0;
   double* gm_V = nullptr;
   double *gm_h = nullptr, *gm_h_host = nullptr, *gm_part = nullptr;
+  // device-resident GMRES recurrence (gmres_kernels.cuh: GmState), as in multigrid.cu
+  GmState* gm_state = nullptr;       // device
+  GmState* gm_state_host = nullptr;  // pinned [GM_RING + 2]
+  double *gm_H = nullptr, *gm_cs = nullptr, *gm_sn = nullptr, *gm_g = nullptr, *gm_yv = nullptr, *gm_red = nullptr;
+  cudaEvent_t gm_ev[GM_RING] = {nullptr};
   int npartials = 0;
   double* red_host = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -880,15 +885,34 @@ static int form_ensure_gmres(lvpp_form_problem* h, int restart) {
   const int64_t cap = (int64_t)(((size_t)24 << 30) / (sizeof(double) * (size_t)h->npad));
   if (restart + 1 > cap) restart = (int)std::max<int64_t>(10, cap - 1);
   if (h->gm_V && restart <= h->gm_restart) return 0;
-  if (h->gm_V) { CKR(fdfree(h, h->gm_V)); CKR(fdfree(h, h->gm_part)); }
+  if (h->gm_V) {
+    CKR(fdfree(h, h->gm_V)); CKR(fdfree(h, h->gm_part));
+    CKR(fdfree(h, h->gm_H)); CKR(fdfree(h, h->gm_cs)); CKR(fdfree(h, h->gm_sn)); CKR(fdfree(h, h->gm_g)); CKR(fdfree(h, h->gm_yv));
+  }
   h->gm_restart = restart;
-  CKR(fdalloc(h, &h->gm_V, (size_t)(restart + 1) * h->npad));
-  CKR(fdalloc(h, &h->gm_part, (size_t)(restart + 4) * h->npartials));
+  const size_t m = (size_t)restart;
+  CKR(fdalloc(h, &h->gm_V, (m + 1) * h->npad));
+  CKR(fdalloc(h, &h->gm_part, (m + 4) * h->npartials));
+  CKR(fdalloc(h, &h->gm_H, (m + 1) * m));
+  CKR(fdalloc(h, &h->gm_cs, m));
+  CKR(fdalloc(h, &h->gm_sn, m));
+  CKR(fdalloc(h, &h->gm_g, m + 1));
+  CKR(fdalloc(h, &h->gm_yv, m));
+  if (!h->gm_state) {
+    CKR(fdalloc(h, &h->gm_state, 1));
+    CKR(fdalloc(h, &h->gm_red, 8));
+    CK(cudaMallocHost((void**)&h->gm_state_host, sizeof(GmState) * (GM_RING + 2)));
+    for (int i = 0; i < GM_RING; ++i) CK(cudaEventCreateWithFlags(&h->gm_ev[i], cudaEventDisableTiming));
+  }
   return 0;
 }
 
-// right-preconditioned restarted GMRES with the block-Jacobi preconditioner (same recurrences as
-// lvpp_gmres_mg in multigrid.cu; vectors are n doubles padded to npad = even, handled as double2)
+// right-preconditioned restarted GMRES with the block-Jacobi preconditioner; vectors are n doubles padded to npad = even,
+// handled as double2.  The recurrence lives on the device exactly as in lvpp_gmres_mg (multigrid.cu): Hessenberg column,
+// Givens rotations, residual estimate, re-orthogonalisation and convergence decisions are taken by one-thread kernels,
+// an iteration is a fixed list of launches with no host round trip, and the host reads a copy of the state one
+// iteration late.  These systems are small (1e5 - 1e6 rows): round 1's six synchronisations per iteration were most of
+// an iteration's time.
 static int form_gmres(lvpp_form_problem* h, const double* d_rhs, double* d_y, const lvpp_newton_opts* o, int32_t* its_out,
                       int32_t* reason_out, double* rnorm_out) {
   CKR(form_ensure_gmres(h, o->ksp_restart));
@@ -899,17 +923,26 @@ static int form_gmres(lvpp_form_problem* h, const double* d_rhs, double* d_y, co
   double* gpart = h->gm_part;
   const int maxit = o->ksp_max_it > 0 ? o->ksp_max_it : 10000;
   CK(cudaEventRecord(h->ev0, h->stream));
-  std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), yv(m);
-  std::vector<double> hh((size_t)m + 8);
   auto vec = [&](int k) { return (double*)(Vb + (int64_t)k * stride2); };
-  int total = 0, reason = 0;
-  double bnorm = 0.0, rnorm = 0.0, tol = 0.0;
-  bool first = true;
+  GmState* st = h->gm_state;
+  GmState* ring = h->gm_state_host;
+  {
+    GmState init;
+    memset(&init, 0, sizeof(init));
+    init.rtol = o->ksp_rtol; init.atol = o->ksp_atol; init.eta2 = 0.5; init.maxit = maxit; init.first = 1;
+    ring[GM_RING + 1] = init;
+    CK(cudaMemcpyAsync(st, &ring[GM_RING + 1], sizeof(GmState), cudaMemcpyHostToDevice, h->stream));
+  }
+  double* hc = h->gm_h + 8;  // dot products / coefficients of the current pass
   CK(cudaMemsetAsync(d_y, 0, sizeof(double) * h->npad, h->stream));
-  double* hdev = h->gm_h + 8;  // coefficient upload area
-  while (reason == 0) {
+  int reason = 0;
+  bool first = true;
+  GmState fin;
+  memset(&fin, 0, sizeof(fin));
+  while (true) {
     if (first) {
       CK(cudaMemcpyAsync(vec(0), d_rhs, sizeof(double) * h->npad, cudaMemcpyDeviceToDevice, h->stream));
+      first = false;
     } else {  // r = rhs - J y (rhs and y are padded work vectors of the handle)
       CKR(form_spmv(h, d_y, vec(0)));
       LAUNCH(h, k_axpby, nb, 256, 0, n2, -1.0, (const double2*)vec(0), 0, (double2*)vec(0));
@@ -917,98 +950,63 @@ static int form_gmres(lvpp_form_problem* h, const double* d_rhs, double* d_y, co
       CK(cudaGetLastError());
     }
     LAUNCH(h, k_multi_dot, nb, 256, 0, n2, Vb, stride2, 0, 1, (const double2*)vec(0), nb, gpart, 1.0);
+    LAUNCH(h, k_reduce_multi, 1, 256, 0, nb, 1, gpart, h->gm_red);
+    LAUNCH(h, k_gm_cycle_begin, 1, 1, 0, st, h->gm_red, h->gm_g, m);
+    LAUNCH(h, k_gm_scale, nb, 256, 0, n2, st, (double2*)vec(0));
     CK(cudaGetLastError());
-    CKR(form_reduce(h, gpart, 1, hh.data()));
-    rnorm = sqrt(hh[0]);
-    if (first) {
-      bnorm = rnorm;
-      tol = std::max(o->ksp_rtol * bnorm, o->ksp_atol);
-      first = false;
-    }
-    if (!std::isfinite(rnorm)) { reason = LVPP_KSP_DIVERGED_NANORINF; break; }
-    if (rnorm <= tol) { reason = rnorm <= o->ksp_atol ? LVPP_KSP_CONVERGED_ATOL : LVPP_KSP_CONVERGED_RTOL; break; }
-    LAUNCH(h, k_axpby, nb, 256, 0, n2, 1.0 / rnorm, (const double2*)vec(0), 0, (double2*)vec(0));
-    CK(cudaGetLastError());
-    std::fill(g.begin(), g.end(), 0.0);
-    g[0] = rnorm;
     int j = 0;
-    for (; j < m; ++j) {
+    bool over = false;
+    for (; j < m && !over; ++j) {
+      const int slot = j % GM_RING;
       CKR(form_precond(h, vec(j), h->z));
       CKR(form_spmv(h, h->z, vec(j + 1)));
-      double* hcol = &H[(size_t)j * (m + 1)];
-      for (int k = 0; k <= j + 1; ++k) hcol[k] = 0.0;
-      double beta = 0.0;
+      double* Hcol = h->gm_H + (size_t)j * (m + 1);
       for (int pass = 0; pass < 2; ++pass) {
         for (int k0 = 0; k0 <= j; k0 += GM_CHUNK) {
           const int nv = std::min(GM_CHUNK, j + 1 - k0);
-          LAUNCH(h, k_multi_dot, nb, 256, 0, n2, Vb, stride2, k0, nv, (const double2*)vec(j + 1), nb, gpart, 1.0);
+          LAUNCH(h, k_multi_dot, nb, 256, 0, n2, Vb, stride2, k0, nv, (const double2*)vec(j + 1), nb, gpart, 1.0, st, pass);
         }
+        LAUNCH(h, k_reduce_multi, (j + 1) < 64 ? (j + 1) : 64, 256, 0, nb, j + 1, gpart, hc, st, pass);
+        LAUNCH(h, k_gmres_update, nb, 256, 0, n2, Vb, stride2, j + 1, hc, (double2*)vec(j + 1), nb, m + 1, gpart, 1.0, st, pass);
+        LAUNCH(h, k_reduce_multi, 1, 256, 0, nb, 1, gpart + (size_t)(m + 1) * nb, h->gm_red + 1, st, pass);
+        LAUNCH(h, k_gm_after_pass, 1, 1, 0, st, j, pass, hc, h->gm_red + 1, Hcol, h->gm_cs, h->gm_sn, h->gm_g);
         CK(cudaGetLastError());
-        LAUNCH(h, k_reduce_multi, (j + 1) < 64 ? (j + 1) : 64, 256, 0, nb, j + 1, gpart, hdev);
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(hh.data(), hdev, sizeof(double) * (j + 1), cudaMemcpyDeviceToHost, h->stream));
-        LAUNCH(h, k_gmres_update, nb, 256, 0, n2, Vb, stride2, j + 1, hdev, (double2*)vec(j + 1), nb, m + 1, gpart, 1.0);
-        CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(h->stream));
-        double hsq = 0.0;
-        for (int k = 0; k <= j; ++k) { hcol[k] += hh[k]; hsq += hh[k] * hh[k]; }
-        double b2 = 0.0;
-        CKR(form_reduce(h, gpart + (size_t)(m + 1) * nb, 1, &b2));
-        beta = sqrt(b2);
-        if (beta * beta > 0.5 * (hsq + beta * beta)) break;
       }
-      hcol[j + 1] = beta;
-      ++total;
-      for (int k = 0; k < j; ++k) {
-        const double t = cs[k] * hcol[k] + sn[k] * hcol[k + 1];
-        hcol[k + 1] = -sn[k] * hcol[k] + cs[k] * hcol[k + 1];
-        hcol[k] = t;
+      LAUNCH(h, k_gm_scale, nb, 256, 0, n2, st, (double2*)vec(j + 1));
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(&ring[slot], st, sizeof(GmState), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaEventRecord(h->gm_ev[slot], h->stream));
+      if (j >= 1) {  // look at iteration j - 1 while iteration j keeps the device busy
+        const int ps = (j - 1) % GM_RING;
+        CK(cudaEventSynchronize(h->gm_ev[ps]));
+        over = ring[ps].conv != 0;
       }
-      const double den = std::hypot(hcol[j], hcol[j + 1]);
-      cs[j] = den > 0 ? hcol[j] / den : 1.0;
-      sn[j] = den > 0 ? hcol[j + 1] / den : 0.0;
-      hcol[j] = den;
-      hcol[j + 1] = 0.0;
-      g[j + 1] = -sn[j] * g[j];
-      g[j] = cs[j] * g[j];
-      rnorm = fabs(g[j + 1]);
-      if (!std::isfinite(rnorm)) { reason = LVPP_KSP_DIVERGED_NANORINF; ++j; break; }
-      const bool conv = rnorm <= tol;
-      if (conv || beta == 0.0 || total >= maxit) {
-        ++j;
-        if (conv) reason = rnorm <= o->ksp_atol ? LVPP_KSP_CONVERGED_ATOL : LVPP_KSP_CONVERGED_RTOL;
-        else if (beta == 0.0) reason = LVPP_KSP_CONVERGED_RTOL;
-        else reason = LVPP_KSP_DIVERGED_ITS;
-        break;
-      }
-      LAUNCH(h, k_axpby, nb, 256, 0, n2, 1.0 / beta, (const double2*)vec(j + 1), 0, (double2*)vec(j + 1));
+    }
+    CK(cudaMemcpyAsync(&ring[GM_RING], st, sizeof(GmState), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    fin = ring[GM_RING];
+    const int k = fin.ncols;
+    if (fin.conv && fin.reason == LVPP_KSP_DIVERGED_NANORINF) { reason = fin.reason; break; }
+    if (k > 0) {
+      LAUNCH(h, k_gm_backsolve, 1, 1, 0, k, m, h->gm_H, h->gm_g, h->gm_yv);
+      double* comb = vec(k);
+      LAUNCH(h, k_lincomb, nb, 256, 0, n2, Vb, stride2, k, h->gm_yv, (double2*)comb);
+      CK(cudaGetLastError());
+      CKR(form_precond(h, comb, h->z));
+      LAUNCH(h, k_axpby, nb, 256, 0, n2, 1.0, (const double2*)h->z, 1, (double2*)d_y);  // y += M^-1 (V yv)
       CK(cudaGetLastError());
     }
-    const int k = j;
-    if (reason == LVPP_KSP_DIVERGED_NANORINF) break;
-    for (int i = k - 1; i >= 0; --i) {
-      double s = g[i];
-      for (int c = i + 1; c < k; ++c) s -= H[(size_t)c * (m + 1) + i] * yv[c];
-      yv[i] = s / H[(size_t)i * (m + 1) + i];
-    }
-    CK(cudaMemcpyAsync(hdev, yv.data(), sizeof(double) * k, cudaMemcpyHostToDevice, h->stream));
-    double* comb = vec(k);
-    LAUNCH(h, k_lincomb, nb, 256, 0, n2, Vb, stride2, k, hdev, (double2*)comb);
-    CK(cudaGetLastError());
-    CKR(form_precond(h, comb, h->z));
-    LAUNCH(h, k_axpby, nb, 256, 0, n2, 1.0, (const double2*)h->z, 1, (double2*)d_y);  // y += M^-1 (V yv)
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(h->stream));
+    if (fin.conv) { reason = fin.reason; break; }
   }
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaEventSynchronize(h->ev1));
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->t_krylov_ms += ms;
-  h->krylov_its += total;
-  if (its_out) *its_out = total;
+  h->krylov_its += fin.total;
+  if (its_out) *its_out = fin.total;
   if (reason_out) *reason_out = reason;
-  if (rnorm_out) *rnorm_out = rnorm;
+  if (rnorm_out) *rnorm_out = fin.rnorm;
   return 0;
 }
 
@@ -1459,6 +1457,9 @@ extern "C" int lvpp_form_destroy(lvpp_form_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& p : h->allocs) cudaFree(p.first);
   if (h->gm_h_host) cudaFreeHost(h->gm_h_host);
+  if (h->gm_state_host) cudaFreeHost(h->gm_state_host);
+  for (int i = 0; i < GM_RING; ++i)
+    if (h->gm_ev[i]) cudaEventDestroy(h->gm_ev[i]);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
