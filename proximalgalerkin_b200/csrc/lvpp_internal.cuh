@@ -210,7 +210,6 @@ struct lvpp_problem {
   int mg_power_boost = 1;         // multiplier of the power iterations (10 while re-estimating after a failed solve)
   int32_t mg_best_its = 0;        // fewest Krylov iterations of a converged solve on this handle (adaptive Chebyshev ratio)
   int64_t mg_retries = 0;         // Krylov solves repeated after a re-estimate
-  int mg_unroll = 4;              // slots per register buffer of k_packed_op (4 or 8)
   bool mg_bf16 = true;            // bf16 pair records (10 B / slot) instead of the single-precision ones (16 B / slot)
   bool mg_cheb_adapt = false;     // LVPP_MG_CHEB_ADAPT=1: fall back to plain damping once a solve needs 1.5x the best count (krylov.cu)
   double mg_cheb = 6.0;           // > 1: Chebyshev-root damping of the sweeps over [b / mg_cheb, b]; else plain damping
@@ -221,8 +220,6 @@ struct lvpp_problem {
   int32_t* coarse_gmap = nullptr; // [V coarsest] global coarse node of every local node
   double* coarse_bg = nullptr;    // [coarse_n] gathered right-hand side
   double* gm_V = nullptr;         // GMRES basis [(restart + 1) * 2V]
-  bool gm_flexible = false;       // experimental (LVPP_GMRES_FLEXIBLE=1): FGMRES, keeps Z_j = M^-1 V_j
-  double* gm_Z = nullptr;         // [restart * 2V] when gm_flexible
   int gm_restart = 0;
   // classical Gram-Schmidt is repeated when less than eta2 of ||w||^2 survives the projection (Daniel et al.)
   double gm_eta2 = 0.01;         // (0.5 = Daniel's criterion; PETSc's default never repeats; profiles/r01_mg_scan.txt)

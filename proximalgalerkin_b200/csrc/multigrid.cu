@@ -681,7 +681,6 @@ int lvpp_mg_setup(lvpp_problem* h) {
   }
   h->mg_cheb = env_double("LVPP_MG_CHEB", h->mg_cheb);
   h->mg_cheb_adapt = env_double("LVPP_MG_CHEB_ADAPT", 0.0) != 0.0;
-  h->mg_unroll = (int)env_double("LVPP_MG_UNROLL", h->mg_unroll);
   h->mg_margin = env_double("LVPP_MG_MARGIN", h->mg_margin);
   h->mg_power_its = (int)env_double("LVPP_MG_POWER_ITS", h->mg_power_its);
   h->gm_eta2 = env_double("LVPP_GMRES_ETA2", h->gm_eta2);
@@ -690,11 +689,6 @@ int lvpp_mg_setup(lvpp_problem* h) {
   h->gm_restart = (int)env_double("LVPP_GMRES_RESTART", 50);
   if (h->gm_restart < 2 || h->gm_restart > 200) { lvpp_set_error("bad LVPP_GMRES_RESTART"); return LVPP_E_INVALID; }
   CKR(lvpp_dalloc(h, &h->gm_V, (size_t)(h->gm_restart + 1) * 2 * h->V));
-  // Flexible GMRES (experimental, off by default): the preconditioned vectors Z_j = M^-1 V_j are kept, the update is
-  // y += Z c instead of y += M^-1 (V c) -- one cycle less per restart, and the cycle may then differ from one
-  // application to the next (a cycle with single-precision vectors: tools/mg_precision.py +fg)
-  h->gm_flexible = env_double("LVPP_GMRES_FLEXIBLE", 0.0) != 0.0;
-  if (h->gm_flexible) CKR(lvpp_dalloc(h, &h->gm_Z, (size_t)h->gm_restart * 2 * h->V));
   CKR(lvpp_dalloc(h, &h->gm_h, (size_t)h->gm_restart + 72));
   {
     const size_t m = (size_t)h->gm_restart;
@@ -818,8 +812,7 @@ static int level_op_local(lvpp_problem* h, MgLevel& L, int epi, double omega, co
     q.skip = h->gm_skip;
     const bool sample = &L == &h->levels[0] && epi == EPI_JACOBI && h->smooth_sample_pending;
     if (sample) CK(cudaEventRecord(h->evp0_cur, h->stream));
-    if (h->mg_unroll == 8) LAUNCH(h, (k_packed2_op<4, 3>), lvpp_grid(L.Vown, 256, 3), 256, 0, q);
-    else LAUNCH(h, (k_packed2_op<2, 4>), lvpp_grid(L.Vown, 256, 4), 256, 0, q);
+    LAUNCH(h, (k_packed2_op<2, 4>), lvpp_grid(L.Vown, 256, 4), 256, 0, q);
     if (&L == &h->levels[0]) h->packed_op_launches++;
     if (sample) {
       CK(cudaEventRecord(h->evp1_cur, h->stream));
@@ -833,8 +826,7 @@ static int level_op_local(lvpp_problem* h, MgLevel& L, int epi, double omega, co
     q.skip = h->gm_skip;
     const bool sample = &L == &h->levels[0] && epi == EPI_JACOBI && h->smooth_sample_pending;
     if (sample) CK(cudaEventRecord(h->evp0_cur, h->stream));
-    if (h->mg_unroll == 8) LAUNCH(h, (k_packed_op<8, 3>), lvpp_grid(L.Vown, 256, 3), 256, 0, q);
-    else LAUNCH(h, (k_packed_op<4, 4>), lvpp_grid(L.Vown, 256, 4), 256, 0, q);
+    LAUNCH(h, (k_packed_op<4, 4>), lvpp_grid(L.Vown, 256, 4), 256, 0, q);
     if (&L == &h->levels[0]) h->packed_op_launches++;
     if (sample) {
       CK(cudaEventRecord(h->evp1_cur, h->stream));
@@ -1193,8 +1185,6 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
       h->smooth_sample_pending = false;
       smooth_rec[slot] = h->smooth_sample_recorded;
       if (rc) { h->gm_skip = nullptr; return rc; }
-      if (h->gm_Z)  // FGMRES: keep Z_j (owned entries; y's ghosts are refreshed by the next residual)
-        CK(cudaMemcpyAsync(h->gm_Z + (size_t)j * 2 * stride2, z, sizeof(double) * 2 * Vown, cudaMemcpyDeviceToDevice, h->stream));
       if (h->nranks > 1) { rc = lvpp_halo_forward_level(h, h->halo, z); if (rc) { h->gm_skip = nullptr; return rc; } }
       CK(cudaEventRecord(h->evs0_ring[slot], h->stream));
       rc = level_op_local(h, L0, EPI_NONE, 1.0, z, nullptr, vec(j + 1));
@@ -1242,17 +1232,11 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
       // back substitution on the device, y += M^-1 (V yv); the combination goes to v_k (v_0..v_{k-1} are the basis)
       LAUNCH(h, k_gm_backsolve, 1, 1, 0, k, m, h->gm_H, h->gm_g, h->gm_yv);
       double* comb = vec(k);
-      if (h->gm_Z) {  // FGMRES: y += Z yv
-        LAUNCH(h, k_lincomb, nb, 256, 0, Vown, (const double2*)h->gm_Z, stride2, k, h->gm_yv, (double2*)comb);
-        CK(cudaGetLastError());
-        LAUNCH(h, k_axpby, nb, 256, 0, Vown, 1.0, (const double2*)comb, 1, (double2*)d_y);
-      } else {
-        LAUNCH(h, k_lincomb, nb, 256, 0, Vown, Vb, stride2, k, h->gm_yv, (double2*)comb);
-        CK(cudaGetLastError());
-        double* z = nullptr;
-        CKR(lvpp_mg_vcycle(h, comb, &z));
-        LAUNCH(h, k_axpby, nb, 256, 0, Vown, 1.0, (const double2*)z, 1, (double2*)d_y);
-      }
+      LAUNCH(h, k_lincomb, nb, 256, 0, Vown, Vb, stride2, k, h->gm_yv, (double2*)comb);
+      CK(cudaGetLastError());
+      double* z = nullptr;
+      CKR(lvpp_mg_vcycle(h, comb, &z));
+      LAUNCH(h, k_axpby, nb, 256, 0, Vown, 1.0, (const double2*)z, 1, (double2*)d_y);
       CK(cudaGetLastError());
     }
     if (fin.conv) { reason = fin.reason; break; }

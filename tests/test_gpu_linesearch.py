@@ -120,10 +120,10 @@ def test_residual_and_jacobian_at_extreme_latent_values(lib):
     assert np.abs(vals[big] - vo[big]).max() <= 1e-9 * np.abs(vo[big]).max()
 
 
-@pytest.mark.parametrize("env", [{}, {"LVPP_GMRES_WEIGHT": "off"}, {"LVPP_GMRES_FLEXIBLE": "1"},
-                                 {"LVPP_GMRES_FLEXIBLE": "1", "LVPP_GMRES_WEIGHT": "off"}, {"LVPP_GMRES_RESTART": "40"}])
+@pytest.mark.parametrize("env", [{}, {"LVPP_GMRES_WEIGHT": "off"}, {"LVPP_GMRES_RESTART": "40"},
+                                 {"LVPP_GMRES_RESTART": "40", "LVPP_GMRES_WEIGHT": "off"}])
 def test_gmres_switches_solve_the_same_system(lib, env, monkeypatch):
-    """The residual norm (equilibrated by default, Euclidean with LVPP_GMRES_WEIGHT=off), flexible GMRES and the
+    """The residual norm (equilibrated by default, Euclidean with LVPP_GMRES_WEIGHT=off) and the
     restart length change the Krylov process, not the solution (restart 40: several cycles, the restart path of the
     device-resident recurrence)."""
     _solve_with_env(env, monkeypatch)
@@ -245,8 +245,7 @@ def test_device_path_against_reference_style_export(lib, case):
         assert np.linalg.norm(uf - g["u_final"]) <= 1e-10 * np.linalg.norm(g["u_final"])
 
 
-@pytest.mark.parametrize("env", [{"LVPP_MG_PACK": "bf16"}, {"LVPP_MG_PACK": "bf16", "LVPP_MG_UNROLL": "8"}, {"LVPP_MG_PACK": "fp32"},
-                                 {"LVPP_MG_PACK": "fp32", "LVPP_MG_UNROLL": "8"}, {"LVPP_MG_FP32": "0"}])
+@pytest.mark.parametrize("env", [{"LVPP_MG_PACK": "bf16"}, {"LVPP_MG_PACK": "fp32"}, {"LVPP_MG_FP32": "0"}])
 def test_cycle_record_formats_precondition_the_same_system(lib, env, monkeypatch):
     """The cycle's copy of the operator: bf16 pair records + single-precision block inverses (the default,
     block_op.cuh:k_packed2_op), single-precision records (LVPP_MG_PACK=fp32, k_packed_op) or the fp64 operator itself

@@ -74,12 +74,12 @@ def test_full_lvpp_solve_mg_matches_oracle(lib, kind, n, degree):
         assert np.allclose(h[key], ho[key], rtol=1e-7, atol=1e-12), key
 
 
-@pytest.mark.parametrize("env", [{"LVPP_MG_CHEB": "0"}, {"LVPP_MG_FP32": "0"}, {"LVPP_MG_UNROLL": "8"},
-                                 {"LVPP_MG_NPRE": "1", "LVPP_MG_NPOST": "3"}])
+@pytest.mark.parametrize("env", [{"LVPP_MG_CHEB": "0"}, {"LVPP_MG_FP32": "0"}, {"LVPP_MG_PACK": "fp32"},
+                                 {"LVPP_MG_NPRE": "2", "LVPP_MG_NPOST": "2"}, {"LVPP_MG_NPRE": "1", "LVPP_MG_NPOST": "3"}])
 def test_mg_variants_solve_the_same_system(lib, env, monkeypatch):
-    """The tunables of the cycle (plain damping instead of Chebyshev roots, fp64 instead of the packed
-    single-precision operator, the other unroll of k_packed_op, unequal pre/post degrees) change the
-    preconditioner, never the solution: read at lvpp_mg_setup time, i.e. per handle."""
+    """The tunables of the cycle (plain damping instead of Chebyshev roots, fp64 or single-precision records instead of
+    the packed bf16 operator, other pre/post degrees) change the preconditioner, never the solution: read at
+    lvpp_mg_setup time, i.e. per handle."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     lvpp, s, dev, orc = _pair("tet", 9, 1)

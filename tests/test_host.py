@@ -158,3 +158,23 @@ def test_product_quadrature_integrates_monomials_exactly(cell, tdim, deg):
         exact = np.prod([factorial(k) for k in e]) / factorial(sum(e) + tdim)
         val = float(np.sum(w * np.prod(p ** np.array(e), axis=1)))
         assert abs(val - exact) <= 2e-15 * max(1.0, 1.0 / exact) * exact + 1e-17, (e, val, exact)
+
+
+def test_clamped_stack_mesh_marks_the_planes_between_the_copies():
+    """bench.py's weak-scaling workload: copies of one box stacked along z, every copy clamped on all six faces --
+    ``create_box(clamp_every=n)`` adds the vertex planes z-index = 0, n, 2n, ... to the Dirichlet set, identically on one
+    rank and on the slabs of a partition."""
+    n, copies = 4, 3
+    kw = dict(lo=(-1.0, -1.0, -float(copies)), hi=(1.0, 1.0, float(copies)), clamp_every=n)
+    whole = lvpp.mesh.create_box(n, n, n * copies, **kw)
+    open_ = lvpp.mesh.create_box(n, n, n * copies, lo=kw["lo"], hi=kw["hi"])
+    extra = np.setdiff1d(whole.boundary_vertices, open_.boundary_vertices)
+    assert extra.size == (copies - 1) * (n - 1) ** 2  # the interior nodes of the two planes between three copies
+    assert np.allclose(np.unique(whole.coords[extra][:, 2]), [-1.0, 1.0])
+    marked = set(whole.global_vertex[whole.boundary_vertices].tolist())
+    for r in range(copies):
+        part = lvpp.mesh.create_box(n, n, n * copies, rank=r, nranks=copies, **kw)
+        assert set(part.global_vertex[part.boundary_vertices].tolist()) <= marked
+        own = part.global_vertex[: part.num_owned_vertices]
+        onb = np.isin(own, part.global_vertex[part.boundary_vertices])
+        assert np.array_equal(np.isin(own, list(marked)), onb)
