@@ -153,6 +153,35 @@ def blas_threads():
         return 1
 
 
+def workload_mesh(args, world):
+    """(dim, n, nxy, nz, lo, hi, slabs) of the N-GPU workload -- shared by both arms."""
+    if args.workload == "obstacle2d":
+        # configs[0]: the 2-D obstacle problem of examples/01 on the unit square mapped to [-1,1]^2, N x N squares with
+        # the right diagonal (SURVEY 8d; N = 1000: 2 004 002 rows); N GPUs: N sqrt(world) squares per axis, y-slabs
+        n = args.n2d
+        nxy = int(round(n * world ** 0.5))
+        return 2, n, nxy, world * max(1, int(round(nxy / world))), None, None, 1
+    nxy, nz, lo, hi, slabs = weak_scaling_mesh(args.n, world, args.weak, args.slabs)
+    return 3, args.n, nxy, nz, lo, hi, slabs
+
+
+def workload_config(args, world):
+    """The part of ``config`` that names the workload: identical in the b200 arm and in the reference arm (which times a
+    bounded sample of it, described in its ``cpu_baseline.sample``)."""
+    dim, n, nxy, nz, lo, hi, slabs = workload_mesh(args, world)
+    rows = 2 * (nxy + 1) ** (dim - 1) * (nz + 1)
+    return {
+        "workload": (f"3-D P1 obstacle LVPP (configs[1]): {nxy}x{nxy}x{nz} cubes x 6 tets, " if dim == 3 else
+                     f"2-D P1 obstacle LVPP (configs[0], examples/01): {nxy}x{nz} squares x 2 triangles on [-1,1]^2, ") + f"{rows} rows",
+        "n": n, "rows": rows, "primal_dofs": rows // 2,  # the reference's CSV column "dofs" (obstacle_pg.py:237,255)
+        "alpha_scheme": args.alpha_scheme, "alpha_max": args.alpha_max, "tol_exit": args.tol_exit, "max_outer": 100,
+        "snes_linesearch_type": "none", "snes_rtol": 1e-6,
+        "parallelism": f"slab{world}", "weak_scaling": (None if world == 1 else args.weak),
+        "obstacle": "phi_set of obstacle_pg.py:92-104" + (", one copy per slab (period 2 in z)" if slabs > 1 else "") +
+                    (", u = 0 on the planes between the slabs" if slabs > 1 and args.weak == "stack" else ""),
+    }
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -166,8 +195,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": nsteps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(nsteps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{dim}-D P1 obstacle LVPP, CPU sample n={n_cpu} ({rows} rows); GPU arm runs n={args.n if dim == 3 else args.n2d} per GPU",
-                   "alpha_scheme": args.alpha_scheme, "alpha_max": args.alpha_max, "tol_exit": args.tol_exit},
+        # the b200 arm's workload; this arm times a bounded sample of it (cpu_baseline.sample) because sparse LU of the
+        # full size is out of reach of any host (3-D, 20 M rows)
+        "config": dict(workload_config(args, int(os.environ.get("WORLD_SIZE", str(max(args.gpus, 1))))),
+                       ksp="sparse LU (SuperLU), the stand-in for ksp_type preonly / pc_type lu / MUMPS (obstacle_pg.py:129-131)",
+                       sample_rows=rows, sample_n=n_cpu),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": blas_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "newton_steps_per_sec": nsteps / secs,
@@ -215,16 +247,10 @@ def run_b200(args):
     # "refine": one obstacle on [-1,1]^3 on a mesh refined so that every GPU keeps ~n^3 cubes (nx = ny =
     # round(n N^(1/3)), nz = the multiple of 2N nearest to nx, N z-slabs).  --slabs S emulates the S-GPU "stack"
     # problem on one GPU (diagnostic).
-    dim = 2 if args.workload == "obstacle2d" else 3
+    dim, n, nxy, nz, lo, hi, slabs = workload_mesh(args, world)
     if dim == 2:
-        # configs[0]: the 2-D obstacle problem of examples/01 on the unit square mapped to [-1,1]^2, N x N squares with
-        # the right diagonal (N = 1000: 2 004 002 rows); N GPUs: N sqrt(world) squares per axis, y-slabs
-        n = args.n2d
-        nxy = int(round(n * world ** 0.5))
-        nz, slabs = world * max(1, int(round(nxy / world))), 1
         msh = lvpp.mesh.create_rectangle(nxy, nz, rank=rank, nranks=world)
     else:
-        nxy, nz, lo, hi, slabs = weak_scaling_mesh(n, world, args.weak, args.slabs)
         msh = lvpp.mesh.create_box(nxy, nxy, nz, lo=lo, hi=hi, rank=rank, nranks=world,
                                    clamp_every=n if (slabs > 1 and args.weak != "stack-open") else None)
     opts = {"ksp_rtol": args.ksp_rtol, "ksp_max_it": 200000}
@@ -429,21 +455,17 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": done, "warmup": args.warmup,
             "ms_per_step": 1e3 * secs / max(done, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": (f"3-D P1 obstacle LVPP (configs[1]): {nxy}x{nxy}x{nz} cubes x 6 tets, " if dim == 3 else
-                                    f"2-D P1 obstacle LVPP (configs[0], examples/01): {nxy}x{nz} squares x 2 triangles on [-1,1]^2, ") +
-                                   f"{rows_global} rows, {stats0['nnz']} nnz/GPU (CSR-equivalent)",
-                       "n": n, "rows": rows_global, "primal_dofs": rows_global // 2,  # the reference's CSV column "dofs" (obstacle_pg.py:237,255)
-                       "alpha_scheme": args.alpha_scheme, "alpha_max": args.alpha_max, "tol_exit": args.tol_exit, "max_outer": 100,
-                       "schedule_note": SCHEDULE_NOTE, "snes_linesearch_type": "none",
-                       "psi_increase_max": args.psi_cap, "psi_free_below": args.psi_free, "snes_rtol": 1e-6, "ksp": ("MINRES + block-Jacobi/Schur-diag" if args.pc == "jacobi" else
-                               "GMRES(50) + monolithic aggregation multigrid V(2,3) (node-block Jacobi sweeps with Chebyshev-root "
-                               "dampings, ratio 6; cycle operator from packed bf16 pair records with fp64 accumulation, fp64 Krylov operator)"), "ksp_rtol": args.ksp_rtol,
-                       "l2": "operator (>=4 GB) and vectors exceed the 126 MB L2; no flush needed" if (dim == 3 and n >= 100) else
-                             ("operator (0.6 GB at N = 1000) and Krylov basis exceed the 126 MB L2; no flush" if dim == 2 and n >= 700 else
-                              "inputs fit L2: kernel-level numbers are L2-warm"),
-                       "parallelism": f"slab{world}", "weak_scaling": (None if world == 1 else args.weak),
-                       "obstacle": "phi_set of obstacle_pg.py:92-104" + (", one copy per slab (period 2 in z)" if slabs > 1 else "") +
-                                   (", u = 0 on the planes between the slabs" if slabs > 1 and args.weak == "stack" else "")},
+            "config": dict(
+                workload_config(args, world),
+                nnz_per_gpu=stats0["nnz"],  # CSR-equivalent
+                schedule_note=SCHEDULE_NOTE, psi_increase_max=args.psi_cap, psi_free_below=args.psi_free,
+                ksp=("MINRES + block-Jacobi/Schur-diag" if args.pc == "jacobi" else
+                     "GMRES(50) + monolithic aggregation multigrid V(2,3) (node-block Jacobi sweeps with Chebyshev-root "
+                     "dampings, ratio 6; cycle operator from packed bf16 pair records with fp64 accumulation, fp64 Krylov operator)"),
+                ksp_rtol=args.ksp_rtol,
+                l2=("operator (>=4 GB) and vectors exceed the 126 MB L2; no flush needed" if (dim == 3 and n >= 100) else
+                    ("operator (0.6 GB at N = 1000) and Krylov basis exceed the 126 MB L2; no flush" if dim == 2 and n >= 700 else
+                     "inputs fit L2: kernel-level numbers are L2-warm"))),
             "newton_steps_per_sec": done / secs, "krylov_iterations": kry, "vcycles": s1["vcycles"] - s0["vcycles"],
             "mg_levels": s1["mg_levels"], "wall_s": wall, "setup_s": t_setup,
             "roofline": roofline, "roofline_jv": roof_extra, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

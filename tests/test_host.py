@@ -178,3 +178,19 @@ def test_clamped_stack_mesh_marks_the_planes_between_the_copies():
         own = part.global_vertex[: part.num_owned_vertices]
         onb = np.isin(own, part.global_vertex[part.boundary_vertices])
         assert np.array_equal(np.isin(own, list(marked)), onb)
+
+
+def test_bench_workload_config_is_shared_by_both_arms():
+    """bench.py: the reference arm reports the b200 arm's workload (it times a bounded sample of it)."""
+    import argparse
+    import importlib
+
+    bench = importlib.import_module("bench")
+    a = argparse.Namespace(workload="obstacle", n=215, n2d=1000, weak="stack", slabs=1, alpha_scheme="constant", alpha_max=1e5,
+                           tol_exit=1e-6)
+    c1 = bench.workload_config(a, 1)
+    assert c1["rows"] == 20155392 and c1["primal_dofs"] == 10077696 and "215x215x215" in c1["workload"]
+    c8 = bench.workload_config(a, 8)
+    assert c8["rows"] == 2 * 216 * 216 * 1721 and "215x215x1720" in c8["workload"] and "u = 0 on the planes" in c8["obstacle"]
+    a.workload = "obstacle2d"
+    assert bench.workload_config(a, 1)["rows"] == 2004002
