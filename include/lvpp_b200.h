@@ -182,6 +182,9 @@ int lvpp_get_csr_pattern(lvpp_handle h, int64_t* h_indptr, int32_t* h_indices);
 int lvpp_set_alpha(lvpp_handle h, double alpha);
 /* f.value = ... : the forcing Constant of obstacle_pg.py:74,122 (dolfinx reads constants at assembly time) */
 int lvpp_set_forcing(lvpp_handle h, double f);
+/* new Dirichlet values g on (a subset of) the Dirichlet nodes given to lvpp_create: a dolfinx DirichletBC reads its
+ * Function / Constant at assembly time (u_bc.x.array[...] = ..., signorini_dolfinx.py:322).  Host arrays. */
+int lvpp_set_bc_values(lvpp_handle h, int64_t num_bc, const int32_t* h_bc_nodes, const double* h_bc_values);
 /* sol_k.x.array[:] = ... (obstacle_pg.py:158,226); d_xk [2*num_nodes] */
 int lvpp_set_previous(lvpp_handle h, const double* d_xk);
 

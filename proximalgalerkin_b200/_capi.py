@@ -180,6 +180,7 @@ SIGNATURES = {
     "lvpp_get_csr_pattern": (C.c_int, [H, c_int64_p, c_int32_p]),
     "lvpp_set_alpha": (C.c_int, [H, C.c_double]),
     "lvpp_set_forcing": (C.c_int, [H, C.c_double]),
+    "lvpp_set_bc_values": (C.c_int, [H, C.c_int64, c_int32_p, c_double_p]),
     "lvpp_get_last_iterate_host": (C.c_int, [H, c_double_p]),
     "lvpp_set_previous": (C.c_int, [H, VP]),
     "lvpp_assemble_residual": (C.c_int, [H, VP, VP, c_double_p]),

@@ -174,6 +174,16 @@ __global__ void k_set_bc(int64_t nbc, const int32_t* __restrict__ nodes, const d
   }
 }
 
+// new values on the Dirichlet nodes given at creation (the flags do not change)
+__global__ void k_set_bc_values(int64_t nbc, const int32_t* __restrict__ nodes, const double* __restrict__ vals,
+                                const uint8_t* __restrict__ flag, double* __restrict__ bcval, int* __restrict__ err) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nbc;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    if (!flag[nodes[p]]) { *err = 1; continue; }
+    bcval[nodes[p]] = vals[p];
+  }
+}
+
 __global__ void k_flag_cols(int64_t nslots, const uint8_t* __restrict__ flag, uint32_t* __restrict__ col) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nslots;
        p += (int64_t)gridDim.x * blockDim.x) {
@@ -589,5 +599,35 @@ extern "C" int lvpp_get_csr_pattern(lvpp_handle h, int64_t* h_indptr, int32_t* h
   CK(cudaStreamSynchronize(h->stream));
   CKR(lvpp_dfree(h, dptr));
   CKR(lvpp_dfree(h, dind));
+  return LVPP_OK;
+}
+
+
+// u_bc.x.array[...] = ... between solves (a dolfinx DirichletBC reads its Function / Constant at assembly time;
+// examples/02_signorini/signorini_dolfinx.py:322 does this, the obstacle driver keeps g = 0): new values g on the
+// Dirichlet nodes given to lvpp_create.  The set of Dirichlet nodes itself is part of the pattern and cannot change.
+extern "C" int lvpp_set_bc_values(lvpp_handle h, int64_t num_bc, const int32_t* h_bc_nodes, const double* h_bc_values) {
+  if (!h) { lvpp_set_error("null handle"); return LVPP_E_INVALID; }
+  if (num_bc < 0 || (num_bc > 0 && (!h_bc_nodes || !h_bc_values))) { lvpp_set_error("null argument"); return LVPP_E_INVALID; }
+  if (num_bc == 0) return LVPP_OK;
+  CK(cudaSetDevice(h->device));
+  for (int64_t p = 0; p < num_bc; ++p)
+    if (h_bc_nodes[p] < 0 || h_bc_nodes[p] >= h->V) { lvpp_set_error("bc node out of range"); return LVPP_E_INVALID; }
+  int32_t* dn = nullptr; double* dv = nullptr; int* derr = nullptr;
+  CKR(lvpp_dalloc(h, &dn, (size_t)num_bc, false));
+  CKR(lvpp_dalloc(h, &dv, (size_t)num_bc, false));
+  CKR(lvpp_dalloc(h, &derr, 1));
+  CK(cudaMemcpyAsync(dn, h_bc_nodes, sizeof(int32_t) * num_bc, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(dv, h_bc_values, sizeof(double) * num_bc, cudaMemcpyHostToDevice, h->stream));
+  LAUNCH(h, k_set_bc_values, lvpp_grid(num_bc, 256), 256, 0, num_bc, dn, dv, h->bc_flag, h->bc_val, derr);
+  CK(cudaGetLastError());
+  int herr = 0;
+  CK(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CKR(lvpp_dfree(h, dn));
+  CKR(lvpp_dfree(h, dv));
+  CKR(lvpp_dfree(h, derr));
+  if (herr) { lvpp_set_error("lvpp_set_bc_values: a node that is not a Dirichlet node of this handle"); return LVPP_E_INVALID; }
+  h->jac_valid = false;  // the residual state of lvpp_newton_begin belongs to the old data
   return LVPP_OK;
 }

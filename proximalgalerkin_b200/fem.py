@@ -244,11 +244,19 @@ class DirichletBC:
         if np.any(self.dofs % 2 != 0):
             raise ValueError("dofs do not belong to V.sub(0)")
         self.nodes = (self.dofs // 2).astype(np.int32)
+        self._source = value  # read again at every solve, like dolfinx reads the bc's Function / Constant at assembly time
+        self.values = self.current_values()
+
+    def current_values(self):
+        """The Dirichlet values as the source object holds them now (a ``Function``, a ``Constant``, an array over the
+        scalar nodes or a scalar)."""
+        value = self._source
         if isinstance(value, Function):
-            self.values = value.x.array[self.dofs].copy()
-        else:
-            v = np.asarray(value, dtype=np.float64)
-            self.values = np.full(self.nodes.size, float(v)) if v.ndim == 0 else v[self.nodes].copy()
+            return value.x.array[self.dofs].copy()
+        if isinstance(value, Constant):
+            return np.full(self.nodes.size, float(value.value))
+        v = np.asarray(value, dtype=np.float64)
+        return np.full(self.nodes.size, float(v)) if v.ndim == 0 else v[self.nodes].copy()
 
 
 def dirichletbc(value, dofs, V):

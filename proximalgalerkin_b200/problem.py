@@ -152,6 +152,7 @@ class DeviceProblem:
         d.qpoints = _capi.as_ptr(arr(V.qpoints, np.float64), C.c_double)
         bc_nodes = np.zeros(0, dtype=np.int32)
         bc_vals = np.zeros(0)
+        self._bcs = list(bcs or [])
         for bc in bcs or []:
             bc_nodes = np.concatenate([bc_nodes, bc.nodes])
             bc_vals = np.concatenate([bc_vals, bc.values])
@@ -241,6 +242,13 @@ class DeviceProblem:
         """Read the form's mutable inputs the way a dolfinx assembly would at call time."""
         self.set_alpha(self.F.alpha.value)
         _capi.check(self.lib.lvpp_set_forcing(self.h, float(self.F.f.value)))
+        for bc in self._bcs:  # Dirichlet values changed since the last push (u_bc.x.array[...] = ...)
+            vals = bc.current_values()
+            if not np.array_equal(vals, bc.values):
+                nodes = np.ascontiguousarray(bc.nodes, dtype=np.int32)
+                vals = np.ascontiguousarray(vals, dtype=np.float64)
+                _capi.check(self.lib.lvpp_set_bc_values(self.h, nodes.size, _capi.as_ptr(nodes, C.c_int32), _capi.as_ptr(vals, C.c_double)))
+                bc.values = vals
         self.set_previous(self.F.sol_k.x.array)
 
     # -- assembly / linear algebra ---------------------------------------------------------------

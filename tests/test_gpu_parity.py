@@ -258,3 +258,38 @@ def test_periodic_obstacle_matches_oracle(lib):
     F1 = lvpp.DeviceVector(d1.n, d1.device)
     d1.assemble_residual(X, F1)
     assert _rel(F1.numpy(), F.numpy()) > 1e-3
+
+
+def test_dirichlet_values_and_forcing_are_read_at_solve_time(lib):
+    """A dolfinx assembly reads Constants and the DirichletBC's Function at call time: mutating ``f.value`` or the bc
+    values between solves changes the next residual (lvpp_set_forcing / lvpp_set_bc_values behind
+    DeviceProblem.sync_coefficients), exactly like the oracle rebuilt with the new data."""
+    import proximalgalerkin_b200 as lvpp
+    from oracle import mesh as omesh
+    from oracle import obstacle as oobs
+
+    n = 6
+    msh = lvpp.mesh.create_box(n, n, n)
+    V = lvpp.fem.functionspace(msh, ("Lagrange", 1))
+    alpha, f = lvpp.fem.Constant(msh, 1.3), lvpp.fem.Constant(msh, 0.0)
+    g = lvpp.fem.Constant(msh, 0.0)
+    dofs = lvpp.fem.locate_dofs_boundary(V.sub(0))
+    bc = lvpp.fem.dirichletbc(value=g, dofs=dofs, V=V.sub(0))
+    sol, sol_k = lvpp.fem.Function(V), lvpp.fem.Function(V)
+    phi = lvpp.fem.QuadratureFunction(V, name="phi")
+    phi.interpolate_phi_set(None, 0.0)
+    F = lvpp.obstacle_residual(sol, sol_k, alpha, f, phi)
+    prob = lvpp.SNESProblem(F, sol, bcs=[bc])
+    dev = prob.device_problem
+    rng = np.random.default_rng(9)
+    x = 0.2 * rng.standard_normal(dev.n)
+    sol_k.x.array[:] = 0.1 * rng.standard_normal(dev.n)
+    X, R = lvpp.DeviceVector(dev.n, dev.device), lvpp.DeviceVector(dev.n, dev.device)
+    X.set(x)
+    for fval, gval in ((0.0, 0.0), (2.5, 0.0), (2.5, -0.3)):
+        f.value, g.value = fval, gval
+        prob.F(None, X, R)
+        orc = oobs.ObstacleOracle(omesh.box_kuhn(n, n, n), f=fval)
+        orc.bc_values[orc.bc_dofs] = gval
+        Fo = orc.assemble_residual(x, sol_k.x.array, alpha.value)
+        assert np.abs(R.numpy() - Fo).max() <= 1e-12 * np.abs(Fo).max(), (fval, gval)
