@@ -204,6 +204,15 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "newton_steps_per_sec": nsteps / secs,
     }
+    if not args.no_aux:
+        # beside the direct-solve port (the reference's algorithm, sequential factorisation): the Krylov path on all host
+        # threads (C + OpenMP assembly + preconditioned MINRES, oracle/c) -- what a CPU user without MUMPS would run
+        try:
+            from oracle import cpu_kernels
+
+            line["cpu_baseline"]["krylov_path"] = cpu_kernels.time_newton_steps_krylov(48 if dim == 3 else 24, 3)
+        except Exception as e:  # optional infrastructure
+            line["cpu_baseline"]["krylov_path"] = {"unavailable": str(e)[:200]}
     print(json.dumps(line))
 
 
