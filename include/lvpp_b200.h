@@ -212,6 +212,10 @@ int lvpp_newton_solve(lvpp_handle h, double* d_x, const lvpp_newton_opts* opts, 
  * begin: evaluates F(x) and the Jacobian; step: solve, update, re-evaluate; returns norms
  * h_norms = {fnorm, ynorm, xnorm} */
 int lvpp_newton_begin(lvpp_handle h, const double* d_x, double* h_fnorm);
+/* same, when d_x is the iterate the previous Newton solve on this handle ended at and only alpha, f, the Dirichlet values
+ * or the previous iterate changed since (the start of the next proximal step, obstacle_pg.py:175-190,226): D(psi) is
+ * kept instead of being re-assembled -- the result is bit-identical to lvpp_newton_begin */
+int lvpp_newton_begin_same_iterate(lvpp_handle h, const double* d_x, double* h_fnorm);
 int lvpp_newton_step(lvpp_handle h, double* d_x, const lvpp_newton_opts* opts, double* h_norms,
                      int32_t* ksp_its, int32_t* ksp_reason);
 

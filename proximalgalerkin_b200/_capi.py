@@ -190,6 +190,7 @@ SIGNATURES = {
     "lvpp_linear_solve": (C.c_int, [H, VP, VP, C.POINTER(NewtonOpts), c_int32_p, c_int32_p, c_double_p]),
     "lvpp_newton_solve": (C.c_int, [H, VP, C.POINTER(NewtonOpts), c_int32_p, c_int32_p, c_double_p, c_int32_p]),
     "lvpp_newton_begin": (C.c_int, [H, VP, c_double_p]),
+    "lvpp_newton_begin_same_iterate": (C.c_int, [H, VP, c_double_p]),
     "lvpp_newton_step": (C.c_int, [H, VP, C.POINTER(NewtonOpts), c_double_p, c_int32_p, c_int32_p]),
     "lvpp_observables": (C.c_int, [H, VP, c_double_p]),
     "lvpp_newton_solve_host": (C.c_int, [H, c_double_p, C.POINTER(NewtonOpts), c_int32_p, c_int32_p, c_double_p, c_int32_p]),

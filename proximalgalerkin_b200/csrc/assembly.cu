@@ -482,9 +482,11 @@ static OpArgs op_args(lvpp_problem* h) {
 }
 
 // F(x) (owned rows) with the Jacobian at x left assembled; ||F||^2 (all ranks) lands in scal->red[0]
-int lvpp_eval_residual(lvpp_problem* h, const double* d_x, double* d_F, bool want_norm) {
+int lvpp_eval_residual(lvpp_problem* h, const double* d_x, double* d_F, bool want_norm, bool keep_D) {
   if (h->nranks > 1) CKR(lvpp_halo_forward_impl(h, const_cast<double*>(d_x)));
-  CKR(assemble_D(h, d_x));
+  // keep_D: d_x is the iterate D(psi) was last assembled at (lvpp_newton_begin_same_iterate) -- only alpha, f, the
+  // Dirichlet values or the previous iterate changed, and D depends on none of them
+  if (!(keep_D && h->jac_valid)) CKR(assemble_D(h, d_x));
   OpArgs p = op_args(h);
   p.v = (const double2*)d_x;
   p.y = (double2*)d_F;

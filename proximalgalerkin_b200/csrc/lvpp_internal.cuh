@@ -360,7 +360,7 @@ __device__ __forceinline__ void stage_tables(double* s_tab, const double* __rest
 // ---- cross-TU entry points --------------------------------------------------------------------
 int lvpp_build_pattern(lvpp_problem* h);                      // setup.cu
 int lvpp_build_constant_operators(lvpp_problem* h, const lvpp_obstacle_desc* d);  // assembly.cu
-int lvpp_eval_residual(lvpp_problem* h, const double* d_x, double* d_F, bool want_norm);  // assembly.cu
+int lvpp_eval_residual(lvpp_problem* h, const double* d_x, double* d_F, bool want_norm, bool keep_D = false);  // assembly.cu
 int lvpp_apply_jacobian(lvpp_problem* h, const double* d_v, double* d_y, const double* inv_scale,
                         double* partials, const int* skip_flag);                    // assembly.cu
 int lvpp_reduce_partials(lvpp_problem* h, int nvals, double* d_out);  // assembly.cu

@@ -55,11 +55,26 @@ static int check_opts(const lvpp_newton_opts* o) {
   return 0;
 }
 
+static int newton_begin(lvpp_handle h, const double* d_x, double* h_fnorm, bool same_iterate);
+
 extern "C" int lvpp_newton_begin(lvpp_handle h, const double* d_x, double* h_fnorm) {
+  return newton_begin(h, d_x, h_fnorm, false);
+}
+
+// The Newton solve of the previous proximal step ended at d_x and nothing but alpha, f, the Dirichlet values or the
+// previous iterate changed since (obstacle_pg.py:175-190,226: `alpha.value = ...; sol_k <- sol; problem.solve()`):
+// D(psi) -- the only part of the Jacobian that depends on the iterate -- is the one of the last residual evaluation and
+// is kept; only the residual is evaluated.  (PETSc re-assembles J(x0) there; the result is bit-identical.)  Falls back
+// to the full evaluation when no Jacobian is valid.
+extern "C" int lvpp_newton_begin_same_iterate(lvpp_handle h, const double* d_x, double* h_fnorm) {
+  return newton_begin(h, d_x, h_fnorm, true);
+}
+
+static int newton_begin(lvpp_handle h, const double* d_x, double* h_fnorm, bool same_iterate) {
   if (!h || !d_x) { lvpp_set_error("null argument"); return LVPP_E_INVALID; }
   CK(cudaSetDevice(h->device));
   CK(cudaEventRecord(h->ev0, h->stream));
-  CKR(lvpp_eval_residual(h, d_x, h->F, true));
+  CKR(lvpp_eval_residual(h, d_x, h->F, true, same_iterate));
   CK(cudaMemcpyAsync(h->red_host, h->scal->red, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaEventRecord(h->ev1, h->stream));
   CKR(lvpp_sync_check_comm(h));

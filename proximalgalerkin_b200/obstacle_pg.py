@@ -188,6 +188,7 @@ class LvppStepper:
         K Newton steps whatever K is, so a solve that finishes inside the timed region is followed by the next one."""
         self.x.tensor.zero_()
         self.xk.tensor.zero_()
+        self._x_is_last_evaluated = False
         self.k = 0  # outer iteration
         self.alpha_value, self.alpha_k = 1.0, 1
         self.newton_its = 0  # within the current outer iteration
@@ -211,7 +212,9 @@ class LvppStepper:
         if self.nb is not None:  # snes_linesearch_type bt: host loop over the library's entry points
             self.fnorm0 = self.nb.begin(self.x)
         else:
-            self.fnorm0 = self.dev.newton_begin(self.x)
+            # after an accepted proximal step x is the iterate of the last residual evaluation: D(psi) is kept
+            self.fnorm0 = self.dev.newton_begin(self.x, same_iterate=self._x_is_last_evaluated)
+            self._x_is_last_evaluated = False
         self.ttol = self.fnorm0 * self.opts.snes_rtol
         self.newton_its = 0
         self.krylov_outer = 0
@@ -285,5 +288,6 @@ class LvppStepper:
         if self.ctl is not None:
             self.ctl.accepted(self.newton_its)
         self.xk.tensor.copy_(self.x.tensor)
+        self._x_is_last_evaluated = self.nb is None  # the library's last residual / Jacobian evaluation was at this x
         self._begin_outer()
         return True

@@ -303,10 +303,13 @@ class DeviceProblem:
         )
         return reason.value, its.value, fn.value, lin.value
 
-    def newton_begin(self, x: DeviceVector):
+    def newton_begin(self, x: DeviceVector, same_iterate=False):
+        """``same_iterate``: ``x`` is where the previous Newton solve on this handle ended and only alpha / f / the
+        Dirichlet values / the previous iterate changed since -- D(psi) is kept (lvpp_newton_begin_same_iterate)."""
         _torch().cuda.current_stream().synchronize()
         fn = C.c_double()
-        _capi.check(self.lib.lvpp_newton_begin(self.h, x.ptr, C.byref(fn)))
+        f = self.lib.lvpp_newton_begin_same_iterate if same_iterate else self.lib.lvpp_newton_begin
+        _capi.check(f(self.h, x.ptr, C.byref(fn)))
         return fn.value
 
     def newton_step(self, x: DeviceVector, opts):

@@ -164,3 +164,30 @@ def test_psi_bound_with_free_rise_converges(lib):
     x1, h1 = run({"lvpp_psi_increase_max": 1.0, "lvpp_psi_free_below": 0.0})
     assert np.linalg.norm(x1[0::2] - x0[0::2]) <= 2e-4 * np.linalg.norm(x0[0::2])
     assert sum(h1["newton_steps"]) <= 3 * sum(h0["newton_steps"])  # (a coarse mesh: psi legitimately rises past 1 early on)
+
+
+def test_keeping_D_at_the_start_of_a_proximal_step_changes_nothing(lib):
+    """lvpp_newton_begin_same_iterate keeps D(psi) when only alpha / the previous iterate changed (the start of every
+    proximal step after the first): histories and the final iterate are bit-identical to re-assembling."""
+    import proximalgalerkin_b200 as lvpp
+
+    def run(reuse):
+        msh = lvpp.mesh.create_box(9, 9, 9)
+        st = lvpp.obstacle_pg.LvppStepper(msh, 1, "double_exponential", 1e2, 1e-4, petsc_options=MG)
+        calls = {"same": 0}
+        inner = st.dev.newton_begin
+
+        def begin(x, same_iterate=False):
+            calls["same"] += bool(same_iterate)
+            return inner(x, same_iterate=same_iterate and reuse)
+
+        st.dev.newton_begin = begin
+        while st.step():
+            pass
+        return st.history, st.x.numpy().copy(), calls["same"]
+
+    h1, x1, n1 = run(True)
+    h0, x0, n0 = run(False)
+    assert n1 == n0 == len(h1["newton_steps"]) - 1  # every proximal step but the first starts from an evaluated iterate
+    assert h1["newton_steps"] == h0["newton_steps"] and h1["krylov_iterations"] == h0["krylov_iterations"]
+    assert h1["primal_increment"] == h0["primal_increment"] and np.array_equal(x1, x0)
