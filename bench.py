@@ -1,19 +1,22 @@
 #!/usr/bin/env python
-"""LVPP Newton-step throughput on B200 (BASELINE.json metric) -- see DESIGN.md section "Measurement".
+"""LVPP Newton-step throughput on B200 (BASELINE.json metric) -- see DESIGN.md section 7 "Measurement".
 
 A "step" is one Newton step of the LVPP obstacle solve (Krylov solve of the saddle-point system,
 fused update + norms, residual and Jacobian assembly at the new iterate; outer-loop work --
 observables, alpha update, sol_k <- sol -- is inside the timed region when it falls between steps).
 Workload at N GPUs: the 3-D P1 obstacle problem on [-1,1]^2 x [-N,N], n x n x (n N) cubes x 6 Kuhn
-tetrahedra, one z-slab per GPU (weak scaling; n = 215 -> 20.2 M rows per GPU), started from the zero
-iterate with the reference's CI parameters (double-exponential alpha, alpha_max 1e2, tol 1e-4,
-SNES rtol 1e-6).  Warm-up steps are the first W Newton steps of that solve; the K timed steps
-continue it.
+tetrahedra, one z-slab, one copy of the obstacle and one clamped box per GPU (weak scaling; n = 215 ->
+20.2 M rows per GPU), started from the zero iterate with the reference script's default parameters
+(obstacle_pg.py:291-321: constant alpha, tol 1e-6, full Newton step, SNES rtol 1e-6).  Warm-up steps are
+the first W Newton steps of that solve; the K timed steps continue it and start a fresh solve when it ends,
+so that exactly K steps are timed whatever K is.  Defaults: --steps 20 --warmup 5.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--size 215] [--impl b200|reference]
+                  [--workload obstacle|obstacle2d|gradient|multiphase|signorini]
 
 --impl reference times the CPU restatement of the reference algorithm (oracle/: numpy assembly +
-SuperLU in place of dolfinx + MUMPS; the real stack is not installable here) on a bounded sample.
+SuperLU in place of dolfinx + MUMPS; the real stack is not installable here) on a bounded sample of the
+same workload, and reports the C + OpenMP Krylov path beside it.
 """
 import argparse
 import json
