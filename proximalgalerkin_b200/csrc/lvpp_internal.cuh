@@ -169,6 +169,7 @@ struct lvpp_problem {
   double* flush = nullptr;      // L2 flush scratch
   size_t flush_bytes = 0;
   bool jac_valid = false;
+  bool y_is_newton_correction = false;  // h->y holds the solution of the last Krylov solve of a Newton step
   // Newton state
   double fnorm = 0.0;
   // stats
@@ -232,6 +233,9 @@ struct lvpp_problem {
   double* gm_red = nullptr;       // device [8] reduced norms
   cudaEvent_t gm_ev[8] = {nullptr};                  // status copy of iteration j landed (ring)
   cudaEvent_t evs0_ring[8] = {nullptr}, evs1_ring[8] = {nullptr}, evp0_ring[8] = {nullptr}, evp1_ring[8] = {nullptr};
+  bool gm_warm = true;            // LVPP_GMRES_WARM=0: every Krylov solve starts from zero
+  bool gm_warm_next = false;      // set by lvpp_newton_step: y still holds the previous Newton correction of this handle
+  int64_t gm_warm_used = 0;       // solves that started from the previous correction
   const int* gm_skip = nullptr;   // non-null inside a GMRES iteration: the large kernels of the cycle return at once when set
   double* gm_h = nullptr;         // device [restart + 2]
   double* gm_h_host = nullptr;    // pinned

@@ -685,6 +685,7 @@ int lvpp_mg_setup(lvpp_problem* h) {
   h->mg_power_its = (int)env_double("LVPP_MG_POWER_ITS", h->mg_power_its);
   h->gm_eta2 = env_double("LVPP_GMRES_ETA2", h->gm_eta2);
   if (const char* gw = getenv("LVPP_GMRES_WEIGHT")) h->gm_weight_auto = strcmp(gw, "off") != 0;
+  h->gm_warm = env_double("LVPP_GMRES_WARM", 1.0) != 0.0;
   // GMRES workspace (also the scratch of the collective decisions below)
   h->gm_restart = (int)env_double("LVPP_GMRES_RESTART", 50);
   if (h->gm_restart < 2 || h->gm_restart > 200) { lvpp_set_error("bad LVPP_GMRES_RESTART"); return LVPP_E_INVALID; }
@@ -1129,15 +1130,35 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
   }
   GmState* st = h->gm_state;
   GmState* ring = h->gm_state_host;            // [0, GM_RING): lagged copies; [GM_RING]: cycle-end copy; [GM_RING + 1]: upload
-  {
-    GmState init;
-    memset(&init, 0, sizeof(init));
-    init.rtol = o->ksp_rtol; init.atol = o->ksp_atol; init.eta2 = h->gm_eta2; init.maxit = maxit; init.first = 1;
-    ring[GM_RING + 1] = init;
-    CK(cudaMemcpyAsync(st, &ring[GM_RING + 1], sizeof(GmState), cudaMemcpyHostToDevice, h->stream));
+  GmState init;
+  memset(&init, 0, sizeof(init));
+  init.rtol = o->ksp_rtol; init.atol = o->ksp_atol; init.eta2 = h->gm_eta2; init.maxit = maxit; init.first = 1;
+  // Warm start (h->gm_warm_next, set by lvpp_newton_step; LVPP_GMRES_WARM=0 disables it): d_y still holds the Newton
+  // correction of the previous solve on this handle.  Late in an LVPP solve consecutive proximal steps take one Newton
+  // step each and their corrections are nearly the same vector (psi falls by alpha lambda on the contact set every
+  // time), so r0 = rhs - J y_prev is orders of magnitude below ||rhs||.  The stopping test stays ||r|| <= rtol ||rhs||
+  // (PETSc's KSPConvergedDefault with a non-zero initial guess); the guess is used only if it is better than zero.
+  bool have_r0 = false;
+  if (h->gm_warm_next && h->gm_warm) {
+    CKR(level_op(h, L0, EPI_RESID, 1.0, d_y, d_rhs, vec(0), false));
+    LAUNCH(h, k_multi_dot, nb, 256, 0, Vown, Vb, stride2, 0, 1, (const double2*)vec(0), nb, gpart, wy);
+    LAUNCH(h, k_multi_dot, nb, 256, 0, Vown, (const double2*)d_rhs, stride2, 0, 1, (const double2*)d_rhs, nb, gpart + nb, wy);
+    CK(cudaGetLastError());
+    CKR(reduce_to_host(h, gpart, 2, h->gm_h, h->gm_h_host));
+    const double r0n = sqrt(h->gm_h_host[0]), bn = sqrt(h->gm_h_host[1]);
+    if (std::isfinite(r0n) && r0n < bn) {
+      have_r0 = true;
+      init.first = 0;
+      init.bnorm = bn;
+      init.tol = std::max(o->ksp_rtol * bn, o->ksp_atol);
+      h->gm_warm_used++;
+    }
   }
+  h->gm_warm_next = false;
+  ring[GM_RING + 1] = init;
+  CK(cudaMemcpyAsync(st, &ring[GM_RING + 1], sizeof(GmState), cudaMemcpyHostToDevice, h->stream));
   const int* skip = &st->conv;
-  CK(cudaMemsetAsync(d_y, 0, sizeof(double) * 2 * h->V, h->stream));
+  if (!have_r0) CK(cudaMemsetAsync(d_y, 0, sizeof(double) * 2 * h->V, h->stream));
   bool smooth_rec[GM_RING] = {false};
   auto take_samples = [&](int slot) -> int {  // the event pairs of a finished iteration
     float sms = 0.f;
@@ -1158,7 +1179,8 @@ int lvpp_gmres_mg(lvpp_problem* h, const double* d_rhs, double* d_y, const lvpp_
   while (true) {
     // r = rhs - J y  (first cycle: y = 0)
     if (first) {
-      CK(cudaMemcpyAsync(vec(0), d_rhs, sizeof(double) * 2 * Vown, cudaMemcpyDeviceToDevice, h->stream));
+      if (!have_r0)  // (warm start: v_0 already holds r0 = rhs - J y_prev)
+        CK(cudaMemcpyAsync(vec(0), d_rhs, sizeof(double) * 2 * Vown, cudaMemcpyDeviceToDevice, h->stream));
       first = false;
     } else {
       CKR(level_op(h, L0, EPI_RESID, 1.0, d_y, d_rhs, vec(0), false));

@@ -93,7 +93,9 @@ extern "C" int lvpp_newton_step(lvpp_handle h, double* d_x, const lvpp_newton_op
   CK(cudaSetDevice(h->device));
   if (!h->jac_valid) { lvpp_set_error("lvpp_newton_begin has not been called"); return LVPP_E_INVALID; }
   int32_t kits = 0, kreason = 0;
+  h->gm_warm_next = h->y_is_newton_correction;  // (multigrid.cu: lvpp_gmres_mg uses it only if it beats the zero guess)
   CKR(lvpp_solve_linear(h, h->F, h->y, opts, &kits, &kreason, nullptr));
+  h->y_is_newton_correction = kreason > 0;
   if (ksp_its) *ksp_its = kits;
   if (ksp_reason) *ksp_reason = kreason;
   CK(cudaEventRecord(h->ev0, h->stream));
